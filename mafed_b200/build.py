@@ -1,0 +1,56 @@
+"""Build the C-ABI shared library in-tree with nvcc (sm_100a only)."""
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB_DIR = os.path.join(PKG, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "libmafed_distill.so")
+SOURCES = [os.path.join(PKG, "csrc", "distill_abi.cu")]
+HEADERS = [os.path.join(PKG, "csrc", n) for n in
+           ("distill_common.cuh", "distill_ldg.cuh", "distill_tma.cuh", "distill_epilogue.cuh",
+            "distill_fused.cuh", "distill_host.cuh")] + \
+          [os.path.join(ROOT, "include", "mafed_distill.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false",
+]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: the CUDA path cannot be built (there is no CPU fallback)")
+    return exe
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.exists(f) and os.path.getmtime(f) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """Compile libmafed_distill.so for sm_100a if missing or older than its sources."""
+    if not force and not is_stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    cmd = [_nvcc()] + flags + ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
+                               "-o", LIB_PATH] + SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,126 @@
+"""ctypes binding of ``include/mafed_distill.h`` (the C ABI under the ``mafed.methods`` mirror).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+MAX_LAYERS = 64
+F32, BF16, F16 = 0, 1, 2
+LOSS_MSE, LOSS_COSINE = 0, 1
+MODW_EQUAL, MODW_TABLE, MODW_CLS, MODW_TEXT_ONLY = 0, 1, 2, 3
+VARIANT_DEFAULT, VARIANT_LDG, VARIANT_TMA = 0, 1, 2
+# keys of mafed_distill_set_tuning (benchmark knobs)
+TUNE_TMA_STAGES, TUNE_TMA_ROWS, TUNE_TMA_WARPS, TUNE_LDG_BLOCKS_PER_SM, TUNE_BWD_REVERSE, TUNE_GRID_MUL = range(6)
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmafed_distill.so")
+
+EXPORTS = (
+    "mafed_distill_abi_version", "mafed_distill_error_string", "mafed_distill_ws_bytes",
+    "mafed_distill_sums_len", "mafed_distill_out_len", "mafed_distill_fwd", "mafed_distill_reduce",
+    "mafed_distill_finalize", "mafed_distill_epilogue", "mafed_distill_bwd", "mafed_distill_set_variant",
+    "mafed_distill_set_tuning",
+)
+
+
+class Shape(ctypes.Structure):
+    """mafed_shape_t"""
+    _fields_ = [(n, ctypes.c_int32) for n in ("n_layers", "B", "T", "n_vis", "D", "dtype", "loss_kind", "cls")]
+
+
+class Weights(ctypes.Structure):
+    """mafed_weights_t"""
+    _fields_ = [
+        ("modality_kind", ctypes.c_int32),
+        ("distill_coeff", ctypes.c_float),
+        ("layer_coeff", ctypes.c_float * MAX_LAYERS),
+        ("lang_weight", ctypes.c_float * MAX_LAYERS),
+    ]
+
+
+class MafedDistillError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Load libmafed_distill.so (built in-tree by ``mafed_b200.build``); raise if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise MafedDistillError(
+                f"{LIB_PATH} not found: build it with `python -m mafed_b200.build` "
+                "(the distillation path has no CPU / eager fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        vp, i32 = ctypes.c_void_p, ctypes.c_int
+        pp = ctypes.POINTER(ctypes.c_void_p)
+        sh, wt = ctypes.POINTER(Shape), ctypes.POINTER(Weights)
+        lib.mafed_distill_abi_version.restype = i32
+        lib.mafed_distill_error_string.restype = ctypes.c_char_p
+        lib.mafed_distill_error_string.argtypes = [i32]
+        lib.mafed_distill_ws_bytes.restype = ctypes.c_size_t
+        lib.mafed_distill_ws_bytes.argtypes = [i32]
+        lib.mafed_distill_sums_len.restype = i32
+        lib.mafed_distill_sums_len.argtypes = [i32]
+        lib.mafed_distill_out_len.restype = i32
+        lib.mafed_distill_out_len.argtypes = [i32]
+        lib.mafed_distill_fwd.restype = i32
+        lib.mafed_distill_fwd.argtypes = [sh, pp, pp, vp, vp, vp]
+        lib.mafed_distill_reduce.restype = i32
+        lib.mafed_distill_reduce.argtypes = [sh, vp, vp, vp, vp]
+        lib.mafed_distill_finalize.restype = i32
+        lib.mafed_distill_finalize.argtypes = [sh, wt, vp, vp, vp, vp]
+        lib.mafed_distill_epilogue.restype = i32
+        lib.mafed_distill_epilogue.argtypes = [sh, wt, vp, vp, vp, vp, vp, vp]
+        lib.mafed_distill_bwd.restype = i32
+        lib.mafed_distill_bwd.argtypes = [sh, pp, pp, pp, vp, vp, vp, vp]
+        lib.mafed_distill_set_variant.restype = i32
+        lib.mafed_distill_set_variant.argtypes = [i32]
+        lib.mafed_distill_set_tuning.restype = i32
+        lib.mafed_distill_set_tuning.argtypes = [i32, i32]
+        for name in EXPORTS:
+            getattr(lib, name)
+        if lib.mafed_distill_abi_version() != 1:
+            raise MafedDistillError("libmafed_distill.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().mafed_distill_error_string(rc).decode()
+        raise MafedDistillError(f"{what} failed: {msg} (code {rc})")
+
+
+def ptr_array(ptrs):
+    """Host array of device pointers (``const void* const*``)."""
+    arr = (ctypes.c_void_p * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def make_shape(n_layers, B, T, n_vis, D, dtype, loss_kind, cls=False):
+    return Shape(n_layers, B, T, n_vis, D, dtype, loss_kind, 1 if cls else 0)
+
+
+def make_weights(modality_kind, distill_coeff, layer_coeffs, lang_weights=None):
+    w = Weights()
+    w.modality_kind = modality_kind
+    w.distill_coeff = float(distill_coeff)
+    for i, c in enumerate(layer_coeffs):
+        w.layer_coeff[i] = float(c)
+    if lang_weights is not None:
+        for i, c in enumerate(lang_weights):
+            w.lang_weight[i] = float(c)
+    return w

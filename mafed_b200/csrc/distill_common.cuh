@@ -1,0 +1,198 @@
+// Shared device helpers for the MAFED distillation kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mafed_distill.h"
+
+namespace mafed {
+
+constexpr int kMaxLayers = MAFED_MAX_LAYERS;
+constexpr float kCosEps = 1e-12f;  // EPSILON of ATen's cosine_embedding_loss
+constexpr int kMaxPartials = 2048;  // upper bound on CTAs writing partial sums
+constexpr int kWsHeaderFloats = 4;  // ws[0] = number of partial blocks (as int)
+
+// Kernel-parameter block shared by forward and backward kernels (passed by value, < 4 KB).
+struct PathParams {
+  const void* s[kMaxLayers];
+  const void* t[kMaxLayers];
+  void* g[kMaxLayers];           // backward only
+  const int64_t* mask;           // [B, txt] int64 (unused in cls mode)
+  float* ws;                     // forward: partial sums
+  const float* bwd_scale;        // backward: [L][2]
+  const float* grad_out;         // backward: device scalar or nullptr
+  long long n_rows;              // rows per layer (B*T, or B in cls mode)
+  long long row_stride;          // elements between consecutive rows
+  int n_layers;
+  int T;                         // positions per sample as seen by the modality rule
+  int n_vis;
+  int txt;                       // T - n_vis
+  int D;
+  int n_chunks;                  // 16-byte chunks per row (vector kernels)
+  int reverse;                   // backward: walk work items last-to-first (L2 reuse after forward)
+};
+
+// ---------------------------------------------------------------- element packing (16-byte vectors)
+template <typename T> struct Pack;
+
+template <> struct Pack<float> {
+  static constexpr int kPer16 = 4;
+  __device__ __forceinline__ static void unpack(const uint4& v, float (&f)[4]) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  __device__ __forceinline__ static uint4 pack(const float (&f)[4]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+  __device__ __forceinline__ static float load1(const void* p, long long i) { return ((const float*)p)[i]; }
+  __device__ __forceinline__ static void store1(void* p, long long i, float v) { ((float*)p)[i] = v; }
+};
+
+template <> struct Pack<__nv_bfloat16> {
+  static constexpr int kPer16 = 8;
+  __device__ __forceinline__ static void unpack(const uint4& v, float (&f)[8]) {
+    // bf16 -> fp32 is exact: the 16 payload bits become the high half of the fp32 word
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+  }
+  __device__ __forceinline__ static uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);  // round-to-nearest-even, once
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+  __device__ __forceinline__ static float load1(const void* p, long long i) {
+    return __bfloat162float(((const __nv_bfloat16*)p)[i]);
+  }
+  __device__ __forceinline__ static void store1(void* p, long long i, float v) {
+    ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  }
+};
+
+template <> struct Pack<__half> {
+  static constexpr int kPer16 = 8;
+  __device__ __forceinline__ static void up2(uint32_t w, float& a, float& b) {
+    float2 r = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    a = r.x; b = r.y;
+  }
+  __device__ __forceinline__ static void unpack(const uint4& v, float (&f)[8]) {
+    up2(v.x, f[0], f[1]); up2(v.y, f[2], f[3]); up2(v.z, f[4], f[5]); up2(v.w, f[6], f[7]);
+  }
+  __device__ __forceinline__ static uint32_t pack2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+  __device__ __forceinline__ static float load1(const void* p, long long i) {
+    return __half2float(((const __half*)p)[i]);
+  }
+  __device__ __forceinline__ static void store1(void* p, long long i, float v) {
+    ((__half*)p)[i] = __float2half_rn(v);
+  }
+};
+
+// ---------------------------------------------------------------- global memory access
+// Streaming 128-bit load: read-only path, do not allocate in L1 (every byte is used exactly once).
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_128(void* p, const uint4& v) {
+  asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------- modality rule
+// distillation.py:134-144: t < n_vis -> visual token, weight 1; else text token weighted by the
+// attention mask value.  Returns the weight; sets `modality` (0 = text, 1 = vision).
+__device__ __forceinline__ float row_weight(const PathParams& p, long long row, int& modality) {
+  const long long b = row / p.T;
+  const int t = (int)(row - b * p.T);
+  if (t < p.n_vis) { modality = 1; return 1.f; }
+  modality = 0;
+  return (float)__ldg(p.mask + b * p.txt + (t - p.n_vis));
+}
+
+// Per-element math.  mse: sum (h-p)^2.  cosine: dot, |h|^2, |p|^2.
+template <int LOSS, int NE>
+__device__ __forceinline__ void accumulate(const float (&a)[NE], const float (&b)[NE], float& x, float& y, float& z) {
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    if (LOSS == MAFED_LOSS_MSE) {
+      const float d = a[i] - b[i];
+      x = fmaf(d, d, x);
+    } else {
+      x = fmaf(a[i], b[i], x);
+      y = fmaf(a[i], a[i], y);
+      z = fmaf(b[i], b[i], z);
+    }
+  }
+}
+
+// Per-row loss value from the warp-reduced statistics.
+template <int LOSS>
+__device__ __forceinline__ float row_value(float x, float y, float z) {
+  if (LOSS == MAFED_LOSS_MSE) return x;  // division by D happens once, in the epilogue
+  const float den = sqrtf((y + kCosEps) * (z + kCosEps));
+  return 1.f - x / den;
+}
+
+// Per-CTA accumulation of [layer][modality] partial sums.  One slot per warp (no atomics: the
+// result is bit-reproducible for a fixed launch geometry), combined in fixed order at kernel end.
+template <int WARPS>
+struct CtaSums {
+  float v[WARPS][kMaxLayers][2];
+};
+
+template <int WARPS>
+__device__ __forceinline__ void cta_sums_zero(CtaSums<WARPS>& s, int n_layers) {
+  for (int i = threadIdx.x; i < WARPS * kMaxLayers * 2; i += blockDim.x) (&s.v[0][0][0])[i] = 0.f;
+}
+
+template <int WARPS>
+__device__ __forceinline__ void cta_sums_flush(CtaSums<WARPS>& s, int warp, int lane, int layer, float text, float vis) {
+  text = warp_sum(text);
+  vis = warp_sum(vis);
+  if (lane == 0 && layer >= 0) {
+    s.v[warp][layer][0] += text;
+    s.v[warp][layer][1] += vis;
+  }
+}
+
+// ws layout: [0..3] header (int n_partials), then [block][layer][2].
+template <int WARPS>
+__device__ __forceinline__ void cta_sums_store(const CtaSums<WARPS>& s, float* ws, int n_layers, int first_thread,
+                                               int n_threads) {
+  if (blockIdx.x == 0 && (int)threadIdx.x == first_thread) reinterpret_cast<int*>(ws)[0] = gridDim.x;
+  float* dst = ws + kWsHeaderFloats + (size_t)blockIdx.x * n_layers * 2;
+  for (int i = (int)threadIdx.x - first_thread; i < n_layers * 2; i += n_threads) {
+    const int l = i >> 1, m = i & 1;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) acc += s.v[w][l][m];
+    dst[i] = acc;
+  }
+}
+
+}  // namespace mafed

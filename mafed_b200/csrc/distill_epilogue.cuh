@@ -1,0 +1,104 @@
+// Single-CTA epilogue: deterministic fp64 reduction of the per-CTA partial sums, mask counts, and
+// the scalar loss algebra of distillation.py:110-120,163 / distillation_loss_weights.py:148-174.
+#pragma once
+#include "distill_common.cuh"
+
+namespace mafed {
+
+constexpr int kEpiThreads = 1024;
+
+struct EpiParams {
+  const float* ws;        // partial sums (reduce phase)
+  const int64_t* mask;    // [B, txt]
+  double* sums;           // [2L + 2]: in (finalize only) / out (reduce)
+  float* out;             // [1 + 3L]
+  float* bwd_scale;       // [2L]
+  long long n_mask;       // B * txt
+  double n_vis_rows;      // B * n_vis (or B in cls mode)
+  int n_layers;
+  int D;
+  int loss_kind;
+  int do_reduce;
+  int do_finalize;
+  mafed_weights_t w;
+};
+
+__global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant__ EpiParams p) {
+  __shared__ double s_sums[2 * kMaxLayers + 2];
+  __shared__ long long s_cnt[kEpiThreads / 32];
+  __shared__ double s_layer[kMaxLayers];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.n_layers;
+
+  if (p.do_reduce) {
+    const int n_part = reinterpret_cast<const int*>(p.ws)[0];
+    const float* part = p.ws + kWsHeaderFloats;
+    // one warp per (layer, modality) pair; lanes stride over the CTA partials in a fixed order
+    for (int pair = warp; pair < 2 * L; pair += kEpiThreads / 32) {
+      double acc = 0.0;
+      for (int b = lane; b < n_part; b += 32) acc += (double)part[(size_t)b * 2 * L + pair];
+      acc = warp_sum(acc);
+      if (lane == 0) s_sums[pair] = acc;
+    }
+    // text-token count = sum of the attention mask (distillation.py:248 `mask.sum()`)
+    long long c = 0;
+    for (long long i = threadIdx.x; i < p.n_mask; i += kEpiThreads) c += p.mask[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_cnt[warp] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long tot = 0;
+      for (int i = 0; i < kEpiThreads / 32; ++i) tot += s_cnt[i];
+      s_sums[2 * L] = (double)tot;
+      s_sums[2 * L + 1] = p.n_vis_rows;
+    }
+    __syncthreads();
+    if (p.sums != nullptr)
+      for (int i = threadIdx.x; i < 2 * L + 2; i += kEpiThreads) p.sums[i] = s_sums[i];
+  } else {
+    for (int i = threadIdx.x; i < 2 * L + 2; i += kEpiThreads) s_sums[i] = p.sums[i];
+    __syncthreads();
+  }
+  if (!p.do_finalize) return;
+
+  const double n_text = s_sums[2 * L], n_vis = s_sums[2 * L + 1];
+  const double k = (p.loss_kind == MAFED_LOSS_MSE) ? 1.0 / (double)p.D : 1.0;
+  for (int l = threadIdx.x; l < L; l += kEpiThreads) {
+    double wt, wv;
+    if (p.w.modality_kind == MAFED_MODW_EQUAL) {
+      wt = (double)(float)(n_text / (n_text + n_vis));
+      wv = (double)(float)(n_vis / (n_text + n_vis));
+    } else if (p.w.modality_kind == MAFED_MODW_TABLE) {
+      wt = (double)p.w.lang_weight[l];
+      wv = (double)(float)(1.0 - wt);
+    } else if (p.w.modality_kind == MAFED_MODW_TEXT_ONLY) {
+      wt = 1.0;
+      wv = 0.0;
+    } else {  // CLS: vision slot only
+      wt = 0.0;
+      wv = 1.0;
+    }
+    const bool cls = p.w.modality_kind == MAFED_MODW_CLS;
+    const bool text_only = p.w.modality_kind == MAFED_MODW_TEXT_ONLY;
+    const double text_loss = cls ? 0.0 : s_sums[2 * l] * k / n_text;  // 0/0 -> NaN, as in the reference
+    const double vis_loss = text_only ? 0.0 : s_sums[2 * l + 1] * k / n_vis;
+    const double layer_loss = cls ? vis_loss : (text_only ? text_loss : wt * text_loss + wv * vis_loss);
+    const double c = (double)p.w.layer_coeff[l] * (double)p.w.distill_coeff;
+    s_layer[l] = c * layer_loss;
+    p.out[1 + l] = (float)layer_loss;
+    p.out[1 + L + 2 * l] = (float)text_loss;
+    p.out[1 + L + 2 * l + 1] = (float)vis_loss;
+    const double g = (p.loss_kind == MAFED_LOSS_MSE) ? 2.0 * k : 1.0;
+    p.bwd_scale[2 * l] = cls ? 0.f : (float)(c * wt * g / n_text);
+    p.bwd_scale[2 * l + 1] = text_only ? 0.f : (float)(c * wv * g / n_vis);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int l = 0; l < L; ++l) tot += s_layer[l];
+    p.out[0] = (float)tot;
+  }
+}
+
+}  // namespace mafed

@@ -1,0 +1,315 @@
+// TMA-staged kernels: one producer warp streams row tiles global -> shared with bulk async copies
+// (cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP) through a multi-stage ring; consumer warps
+// read the staged rows with conflict-free 128-bit shared loads.  One persistent CTA per SM; the ring
+// keeps up to ~190 KB per SM in flight without spending registers on it.
+#pragma once
+#include "distill_common.cuh"
+
+namespace mafed {
+
+constexpr int kTmaMaxStages = 8;
+constexpr int kTmaMaxRows = 32;  // rows per stage (one per producer lane)
+
+struct TmaGeom {
+  int stages;
+  int rows;         // rows per stage
+  int stage_bytes;  // 2 * rows * row_bytes
+};
+
+struct TmaStageMeta {
+  float w[kTmaMaxRows];
+  int mod[kTmaMaxRows];
+  int layer;
+  int n_rows;
+  long long row0;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds_128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n_threads) : "memory");
+}
+
+// ---------------------------------------------------------------- producer
+// All 32 lanes of the producer warp run this; lane r owns row r of every stage.
+template <typename T>
+__device__ __forceinline__ void tma_producer(const PathParams& p, const TmaGeom& geo, unsigned char* data,
+                                             uint64_t* full, uint64_t* empty, TmaStageMeta* meta, int lane,
+                                             bool for_backward) {
+  const long long tiles_per_layer = (p.n_rows + geo.rows - 1) / geo.rows;
+  const long long total = tiles_per_layer * p.n_layers;
+  const uint32_t row_bytes = (uint32_t)p.n_chunks * 16u;
+  const long long row_pitch = p.row_stride * (long long)sizeof(T);
+  const bool contiguous = row_pitch == (long long)row_bytes;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (long long t0 = blockIdx.x; t0 < total; t0 += gridDim.x) {
+    const long long tile = p.reverse ? (total - 1 - t0) : t0;
+    const int l = (int)(tile / tiles_per_layer);
+    const long long row0 = (tile - (long long)l * tiles_per_layer) * geo.rows;
+    const int n_rows = (int)min((long long)geo.rows, p.n_rows - row0);
+    mbar_wait(smem_u32(&empty[stage]), phase ^ 1u);  // slot free (first lap passes immediately)
+
+    int m = 1;
+    float w = 0.f;
+    if (lane < n_rows) w = row_weight(p, row0 + lane, m);
+    if (for_backward && p.g[l] == nullptr) w = 0.f;
+    const unsigned valid = __ballot_sync(0xffffffffu, w != 0.f);
+    TmaStageMeta& mt = meta[stage];
+    mt.w[lane] = w;
+    mt.mod[lane] = m;
+    if (lane == 0) { mt.layer = l; mt.n_rows = n_rows; mt.row0 = row0; }
+    __syncwarp();
+    const uint32_t bar = smem_u32(&full[stage]);
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)__popc(valid) * 2u * row_bytes);
+    __syncwarp();
+    const uint32_t s_dst = smem_u32(data + (size_t)stage * geo.stage_bytes);
+    const uint32_t t_dst = s_dst + (uint32_t)geo.rows * row_bytes;
+    const char* sb = reinterpret_cast<const char*>(p.s[l]) + row0 * row_pitch;
+    const char* tb = reinterpret_cast<const char*>(p.t[l]) + row0 * row_pitch;
+    const unsigned all = (n_rows >= 32) ? 0xffffffffu : ((1u << n_rows) - 1u);
+    if (contiguous && valid == all) {
+      // whole tile live: one bulk copy per tensor
+      if (lane == 0) bulk_g2s(s_dst, sb, (uint32_t)n_rows * row_bytes, bar);
+      if (lane == 1) bulk_g2s(t_dst, tb, (uint32_t)n_rows * row_bytes, bar);
+    } else if (w != 0.f) {
+      // ragged tile: only live rows are fetched (padded text rows cost no bandwidth)
+      bulk_g2s(s_dst + (uint32_t)lane * row_bytes, sb + (long long)lane * row_pitch, row_bytes, bar);
+      bulk_g2s(t_dst + (uint32_t)lane * row_bytes, tb + (long long)lane * row_pitch, row_bytes, bar);
+    }
+    if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
+  }
+}
+
+struct TmaSmem {
+  uint64_t full[kTmaMaxStages];
+  uint64_t empty[kTmaMaxStages];
+  TmaStageMeta meta[kTmaMaxStages];
+};
+
+template <int NCW>
+__device__ __forceinline__ void tma_prologue(TmaSmem& sm, const TmaGeom& geo) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < geo.stages; ++i) {
+      mbar_init(smem_u32(&sm.full[i]), 1);      // producer's arrive.expect_tx
+      mbar_init(smem_u32(&sm.empty[i]), NCW);   // one arrive per consumer warp
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------- forward
+template <typename T, int LOSS, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1)
+k_fwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom geo) {
+  constexpr int NE = Pack<T>::kPer16;
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ TmaSmem sm;
+  __shared__ CtaSums<NCW> sums;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cta_sums_zero(sums, p.n_layers);
+  tma_prologue<NCW>(sm, geo);
+
+  if (warp == NCW) {
+    tma_producer<T>(p, geo, dyn_smem, sm.full, sm.empty, sm.meta, lane, false);
+    return;
+  }
+  const long long tiles_per_layer = (p.n_rows + geo.rows - 1) / geo.rows;
+  const long long total = tiles_per_layer * p.n_layers;
+  const uint32_t row_bytes = (uint32_t)p.n_chunks * 16u;
+  float acc_text = 0.f, acc_vis = 0.f;
+  int cur = -1, stage = 0;
+  uint32_t phase = 0;
+  long long it = 0;
+  for (long long t0 = blockIdx.x; t0 < total; t0 += gridDim.x, ++it) {
+    mbar_wait(smem_u32(&sm.full[stage]), phase);
+    const TmaStageMeta& mt = sm.meta[stage];
+    const int l = mt.layer;
+    if (l != cur) {
+      cta_sums_flush(sums, warp, lane, cur, acc_text, acc_vis);
+      acc_text = acc_vis = 0.f;
+      cur = l;
+    }
+    const uint32_t s_base = smem_u32(dyn_smem + (size_t)stage * geo.stage_bytes);
+    const uint32_t t_base = s_base + (uint32_t)geo.rows * row_bytes;
+    // rotate the row->warp map with the iteration so short tiles still use every warp over time
+    const int first = (int)((warp + NCW - (int)((it * geo.rows) % NCW)) % NCW);
+    for (int r = first; r < mt.n_rows; r += NCW) {
+      const float w = mt.w[r];
+      if (w == 0.f) continue;
+      const uint32_t sa = s_base + (uint32_t)r * row_bytes, ta = t_base + (uint32_t)r * row_bytes;
+      float x = 0.f, y = 0.f, z = 0.f;
+      int c = lane;
+      for (; c + 96 < p.n_chunks; c += 128) {
+        uint4 sv[4], tv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          sv[u] = lds_128(sa + (uint32_t)(c + 32 * u) * 16u);
+          tv[u] = lds_128(ta + (uint32_t)(c + 32 * u) * 16u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float a[NE], b[NE];
+          Pack<T>::unpack(sv[u], a);
+          Pack<T>::unpack(tv[u], b);
+          accumulate<LOSS, NE>(a, b, x, y, z);
+        }
+      }
+      for (; c < p.n_chunks; c += 32) {
+        float a[NE], b[NE];
+        Pack<T>::unpack(lds_128(sa + (uint32_t)c * 16u), a);
+        Pack<T>::unpack(lds_128(ta + (uint32_t)c * 16u), b);
+        accumulate<LOSS, NE>(a, b, x, y, z);
+      }
+      float val;
+      if (LOSS == MAFED_LOSS_MSE) {
+        val = x;
+      } else {
+        x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
+        val = (lane == 0) ? row_value<LOSS>(x, y, z) : 0.f;
+      }
+      if (mt.mod[r] == 0) acc_text = fmaf(w, val, acc_text);
+      else acc_vis = fmaf(w, val, acc_vis);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stage]));
+    if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
+  }
+  cta_sums_flush(sums, warp, lane, cur, acc_text, acc_vis);
+  named_bar_sync(1, NCW * 32);
+  cta_sums_store(sums, p.ws, p.n_layers, 0, NCW * 32);
+}
+
+// ---------------------------------------------------------------- backward
+template <int LOSS, int NE>
+__device__ __forceinline__ void grad_elems_tma(const float (&a)[NE], const float (&b)[NE], float scale, float ch,
+                                               float cp, float (&o)[NE]) {
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    if (LOSS == MAFED_LOSS_MSE) o[i] = scale * (a[i] - b[i]);
+    else o[i] = fmaf(ch, a[i], -cp * b[i]);
+  }
+}
+
+template <typename T, int LOSS, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1)
+k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom geo) {
+  constexpr int NE = Pack<T>::kPer16;
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ TmaSmem sm;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tma_prologue<NCW>(sm, geo);
+  if (warp == NCW) {
+    tma_producer<T>(p, geo, dyn_smem, sm.full, sm.empty, sm.meta, lane, true);
+    return;
+  }
+  const long long tiles_per_layer = (p.n_rows + geo.rows - 1) / geo.rows;
+  const long long total = tiles_per_layer * p.n_layers;
+  const uint32_t row_bytes = (uint32_t)p.n_chunks * 16u;
+  const long long row_pitch = p.row_stride * (long long)sizeof(T);
+  const float gout = p.grad_out ? __ldg(p.grad_out) : 1.f;
+  int stage = 0;
+  uint32_t phase = 0;
+  long long it = 0;
+  for (long long t0 = blockIdx.x; t0 < total; t0 += gridDim.x, ++it) {
+    mbar_wait(smem_u32(&sm.full[stage]), phase);
+    const TmaStageMeta& mt = sm.meta[stage];
+    const int l = mt.layer;
+    char* gb = reinterpret_cast<char*>(p.g[l]);
+    const uint32_t s_base = smem_u32(dyn_smem + (size_t)stage * geo.stage_bytes);
+    const uint32_t t_base = s_base + (uint32_t)geo.rows * row_bytes;
+    const int first = (int)((warp + NCW - (int)((it * geo.rows) % NCW)) % NCW);
+    if (gb != nullptr) {
+      for (int r = first; r < mt.n_rows; r += NCW) {
+        char* grow = gb + (mt.row0 + r) * row_pitch;
+        const float w = mt.w[r] * gout * __ldg(p.bwd_scale + 2 * l + mt.mod[r]);
+        if (mt.w[r] == 0.f) {  // padded text row: nothing was fetched; grad = 0 * scale (zero, or NaN if scale is)
+          float o[NE];
+#pragma unroll
+          for (int i = 0; i < NE; ++i) o[i] = w;
+          const uint4 fill = Pack<T>::pack(o);
+          for (int c = lane; c < p.n_chunks; c += 32) stg_128(grow + (long long)c * 16, fill);
+          continue;
+        }
+        const uint32_t sa = s_base + (uint32_t)r * row_bytes, ta = t_base + (uint32_t)r * row_bytes;
+        float ch = 0.f, cp = 0.f;
+        if (LOSS == MAFED_LOSS_COSINE) {
+          float x = 0.f, y = 0.f, z = 0.f;
+          for (int c = lane; c < p.n_chunks; c += 32) {
+            float a[NE], b[NE];
+            Pack<T>::unpack(lds_128(sa + (uint32_t)c * 16u), a);
+            Pack<T>::unpack(lds_128(ta + (uint32_t)c * 16u), b);
+            accumulate<LOSS, NE>(a, b, x, y, z);
+          }
+          x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
+          const float aa = y + kCosEps, den = sqrtf(aa * (z + kCosEps));
+          ch = w * (x / den) / aa;
+          cp = w / den;
+        }
+        int c = lane;
+        for (; c + 96 < p.n_chunks; c += 128) {
+          uint4 sv[4], tv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            sv[u] = lds_128(sa + (uint32_t)(c + 32 * u) * 16u);
+            tv[u] = lds_128(ta + (uint32_t)(c + 32 * u) * 16u);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float a[NE], b[NE], o[NE];
+            Pack<T>::unpack(sv[u], a);
+            Pack<T>::unpack(tv[u], b);
+            grad_elems_tma<LOSS, NE>(a, b, w, ch, cp, o);
+            stg_128(grow + (long long)(c + 32 * u) * 16, Pack<T>::pack(o));
+          }
+        }
+        for (; c < p.n_chunks; c += 32) {
+          float a[NE], b[NE], o[NE];
+          Pack<T>::unpack(lds_128(sa + (uint32_t)c * 16u), a);
+          Pack<T>::unpack(lds_128(ta + (uint32_t)c * 16u), b);
+          grad_elems_tma<LOSS, NE>(a, b, w, ch, cp, o);
+          stg_128(grow + (long long)c * 16, Pack<T>::pack(o));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stage]));
+    if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
+  }
+}
+
+}  // namespace mafed

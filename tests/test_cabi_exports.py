@@ -1,0 +1,46 @@
+"""The C-ABI library builds for sm_100a, loads, and exports every symbol the header declares (not gpu)."""
+import ctypes
+import os
+import re
+import subprocess
+
+from mafed_b200 import build, cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "mafed_distill.h")).read()
+    return sorted(set(re.findall(r"\b(mafed_distill_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    build.build()
+    lib = cabi.load()
+    names = _declared()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(cabi.EXPORTS) == names
+    assert lib.mafed_distill_abi_version() == 1
+    assert lib.mafed_distill_sums_len(15) == 32 and lib.mafed_distill_out_len(15) == 46
+    assert lib.mafed_distill_ws_bytes(15) >= 148 * 15 * 2 * 4
+    assert b"invalid argument" in lib.mafed_distill_error_string(-1)
+
+
+def test_argument_errors_without_a_gpu():
+    lib = cabi.load()
+    bad = cabi.make_shape(0, 1, 1, 0, 8, cabi.F32, cabi.LOSS_MSE)
+    assert lib.mafed_distill_fwd(ctypes.byref(bad), None, None, None, None, None) == -1
+    bad = cabi.make_shape(1, 1, 4, 2, 8, 7, cabi.LOSS_MSE)
+    assert lib.mafed_distill_fwd(ctypes.byref(bad), None, None, None, None, None) == -2
+    ok = cabi.make_shape(1, 1, 4, 2, 8, cabi.F32, cabi.LOSS_MSE)
+    assert lib.mafed_distill_fwd(ctypes.byref(ok), None, None, None, None, None) == -1  # null pointer tables
+    assert lib.mafed_distill_set_variant(9) == -1
+
+
+def test_sass_is_sm100_and_uses_bulk_copies():
+    out = subprocess.run(["cuobjdump", "-sass", cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out or "sm_100" in out
+    assert "UBLKCP" in out  # cp.async.bulk (TMA engine) in the staged kernels
+    assert re.search(r"LDG\.E(\.NA)?\.128", out) and "STG.E.128" in out and "LDS.128" in out

@@ -1,0 +1,115 @@
+"""BASELINE.json's full sizes (C2, C3-lite, C4 per-GPU shard): size-independent properties plus a plain
+PyTorch fp32 restatement of the same op evaluated on the GPU layer by layer."""
+import pytest
+import torch
+
+from gpu_util import Out, make_method, rel_err
+from mafed_b200 import cabi
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = {
+    # name: (tuple_len, num_hidden_layers (ref rule L-1), B, txt, D)
+    "C2-base-b128": (13, 11, 128, 32, 768),
+    "C4-1b-shard-b64": (17, 15, 64, 32, 2048),
+}
+
+
+def _inputs(cfg, dtype=torch.bfloat16, seed=1234, ragged=True):
+    n_tuple, nh, B, txt, D = cfg
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    st, te = [], []
+    for i in range(n_tuple):
+        if i >= nh:  # un-selected tail of the tuple: keep it tiny, the path must not touch it
+            st.append(torch.zeros(1, device="cuda", dtype=dtype)); te.append(st[-1]); continue
+        s = torch.randn(B, 256 + txt, D, generator=g, device="cuda", dtype=torch.float32)
+        t = s + 0.1 * torch.randn(B, 256 + txt, D, generator=g, device="cuda", dtype=torch.float32)
+        st.append(s.to(dtype)); te.append(t.to(dtype))
+    am = torch.ones(B, txt, dtype=torch.int64, device="cuda")
+    if ragged:
+        for b in range(B):
+            am[b, : txt - (1 + (7 * b) % txt)] = 0
+    return st, te, am
+
+
+def _run(meta, st, te, am, grad_out=1.0, variant=cabi.VARIANT_DEFAULT):
+    cabi.load().mafed_distill_set_variant(variant)
+    try:
+        fd = make_method(meta)
+        leaves = [s.detach().requires_grad_(True) for s in st]
+        fd.past_model = lambda **kw: Out(tuple(te))
+        loss = fd.distill(Out(tuple(leaves)), {"attention_mask": am})
+        (loss * grad_out).backward()
+        torch.cuda.synchronize()
+        return loss.detach(), [l.grad for l in leaves], fd
+    finally:
+        cabi.load().mafed_distill_set_variant(cabi.VARIANT_DEFAULT)
+
+
+def _torch_reference(meta, st, te, am, nh, gamma=0.5):
+    """SURVEY 3.3 formulae with plain torch fp32 ops on the GPU (balanced / discounted / mse)."""
+    B, txt = am.shape
+    w_text = torch.cat([torch.zeros(B, 256, device="cuda"), am.float()], 1)
+    w_vis = torch.cat([torch.ones(B, 256, device="cuda"), torch.zeros(B, txt, device="cuda")], 1)
+    coeffs = torch.tensor([gamma ** d for d in range(nh, 0, -1)], dtype=torch.float64)
+    coeffs = (coeffs / coeffs.sum()).tolist()
+    total, grads = 0.0, []
+    for l in range(nh):
+        d = st[l].float() - te[l].float()
+        D = d.shape[-1]
+        tok = d.pow(2).sum(-1).double() / D
+        lt = (tok * w_text).sum() / w_text.sum()
+        lv = (tok * w_vis).sum() / w_vis.sum()
+        total = total + coeffs[l] * (0.5 * lt + 0.5 * lv)
+        row = coeffs[l] * 0.5 * (w_text / w_text.sum() + w_vis / w_vis.sum()) * 2.0 / D
+        grads.append((d * row.float().unsqueeze(-1)))
+    return float(total), grads
+
+
+META = dict(modality="balanced", layer_strategy="discounted", loss="mse", gamma=0.5, layer=None, n_vis=256)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("variant", [cabi.VARIANT_LDG, cabi.VARIANT_TMA], ids=["ldg", "tma"])
+def test_fullsize_against_torch_fp32(name, variant):
+    cfg = CONFIGS[name]
+    nh = cfg[1]
+    st, te, am = _inputs(cfg)
+    loss, grads, _ = _run(dict(META, num_hidden_layers=nh), st, te, am, variant=variant)
+    want, ref_grads = _torch_reference(META, st, te, am, nh)
+    assert float(loss) == pytest.approx(want, rel=2e-3)       # bf16-input tolerance of the north_star
+    assert float(loss) == pytest.approx(want, rel=1e-5)       # ... and in fact fp32-tight: inputs are exact in fp32
+    for l in range(nh):
+        assert rel_err(grads[l].float(), ref_grads[l]) < 2e-3
+        # padded text rows are exactly zero
+        pad = torch.cat([torch.zeros_like(am[:, :1]).expand(-1, 256), am], 1) == 0
+        pad[:, :256] = False
+        assert float(grads[l][pad].abs().max()) == 0.0
+    assert all(g is None for g in grads[nh:])
+
+
+def test_fullsize_properties_c4_shard():
+    cfg = CONFIGS["C4-1b-shard-b64"]
+    nh = cfg[1]
+    meta = dict(META, num_hidden_layers=nh)
+    st, te, am = _inputs(cfg)
+    loss1, g1, _ = _run(meta, st, te, am)
+    loss2, g2, _ = _run(meta, st, te, am)
+    # bit-reproducible: no atomics anywhere in the reduction
+    assert torch.equal(loss1, loss2) and all(torch.equal(a, b) for a, b in zip(g1[:nh], g2[:nh]))
+    # linear in the upstream gradient (a power of two scales bf16 exactly)
+    _, gh, _ = _run(meta, st, te, am, grad_out=0.5)
+    assert all(torch.equal(a * 0.5, b) for a, b in zip(g1[:nh], gh[:nh]))
+    # teacher == student: zero loss and zero gradient
+    loss0, g0, _ = _run(meta, st, st, am)
+    assert float(loss0) == 0.0 and all(float(g.abs().max()) == 0.0 for g in g0[:nh])
+    # both kernel families agree
+    la, ga, _ = _run(meta, st, te, am, variant=cabi.VARIANT_LDG)
+    lb, gb, _ = _run(meta, st, te, am, variant=cabi.VARIANT_TMA)
+    assert float(la) == pytest.approx(float(lb), rel=1e-6)
+    assert all(rel_err(a.float(), b.float()) < 1e-3 for a, b in zip(ga[:nh], gb[:nh]))
+    # loss is additive over layers: sum of logged layer losses x coefficients == total
+    _, _, fd = _run(meta, st, te, am)
+    coeffs = [float(fd.loss_weights.get_layer_loss_weight(l)) for l in range(nh)]
+    per_layer = fd.last_layer_losses[:nh].double().cpu()
+    assert float((per_layer * torch.tensor(coeffs, dtype=torch.float64)).sum()) == pytest.approx(float(loss1), rel=1e-6)

@@ -1,0 +1,227 @@
+"""Parity of the sm_100a path against the reference-generated golden vectors and the CPU oracle.
+
+Everything here calls the CUDA kernels through the C ABI (ctypes) via the mirrored
+``mafed.methods`` API.  Tolerances are the north_star's: 1e-5 relative (fp32), 2e-3 (bf16/fp16).
+"""
+import pytest
+import torch
+
+from golden_util import case_id, load_cases, oracle_cfg
+from gpu_util import rel_err, run_product, tolerances
+from mafed_b200 import cabi
+from oracle import distill_oracle as O
+
+pytestmark = pytest.mark.gpu
+CASES = load_cases()
+VARIANTS = [("ldg", cabi.VARIANT_LDG), ("tma", cabi.VARIANT_TMA)]
+
+
+def _check(out, ref_loss, ref_grads, dtype, layer_losses=None):
+    ltol, gtol = tolerances(dtype)
+    assert float(out["loss"]) == pytest.approx(float(ref_loss), rel=ltol, abs=1e-12)
+    got_sel = [i for i, g in enumerate(out["grads"]) if g is not None]
+    ref_sel = [i for i, g in enumerate(ref_grads) if g is not None]
+    assert got_sel == ref_sel
+    for i in ref_sel:
+        g, r = out["grads"][i], ref_grads[i]
+        assert g.dtype == dtype and g.shape == r.shape
+        assert rel_err(g.float(), r.float()) <= gtol
+        # zero exactly where the reference is zero (padded text positions)
+        zero_rows = (r.float().abs().amax(-1) == 0)
+        assert bool((g.float().abs().amax(-1)[zero_rows] == 0).all())
+        if dtype == torch.float32:
+            torch.testing.assert_close(g, r, rtol=1e-5, atol=1e-5 * float(r.abs().max()))
+    if layer_losses:
+        for k, v in layer_losses.items():
+            assert out["layer_dict"][k] == pytest.approx(v, rel=ltol)
+
+
+@pytest.mark.parametrize("vname,variant", VARIANTS)
+@pytest.mark.parametrize("case", CASES, ids=[case_id(c) for c in CASES])
+def test_golden_vectors(case, vname, variant):
+    m = case["meta"]
+    dtype = case["students"][0].dtype
+    out = run_product(m, case["students"], case["teachers"], case["mask"], grad_out=m["grad_out"], variant=variant)
+    grads = [None] * len(case["students"])
+    for j, g in zip(case["grad_layers"], case["grads"]):
+        grads[j] = g.to(dtype)
+    logged = {f"task_0/distill_loss_{l}": v for l, v in zip(case["logged_layers"], case["logged"])}
+    _check(out, case["loss"], grads, dtype, logged if not m["cls"] else None)
+    if not m["cls"]:  # side effects on `batch` (distillation.py:139,144,221)
+        b = out["batch"]
+        assert "labels" not in b and b["lang_masks"].shape == b["image_masks"].shape == (m["bsz"], m["n_vis"] + m["txt"])
+        assert int(b["image_masks"].sum()) == m["bsz"] * m["n_vis"]
+        assert int(b["lang_masks"].sum()) == int(case["mask"].sum())
+    assert out["fd"].step == 1
+
+
+SHAPES = [
+    # name, n_tuple, nh, B, txt, D, dtype, loss, modality, layer_strategy
+    ("C1-base-fp32", 13, 11, 8, 32, 768, torch.float32, "mse", "balanced", "discounted"),
+    ("C1-base-fp32-equal-cos", 13, 11, 8, 32, 768, torch.float32, "cosine", "equal", "discounted"),
+    ("base-bf16", 13, 11, 6, 32, 768, torch.bfloat16, "mse", "balanced", "discounted"),
+    ("410m-bf16", 7, 5, 5, 17, 1024, torch.bfloat16, "mse", "equal", "equal"),
+    ("1b-bf16", 5, 4, 4, 32, 2048, torch.bfloat16, "mse", "balanced", "discounted"),
+    ("1b-bf16-cos", 5, 4, 3, 9, 2048, torch.bfloat16, "cosine", "balanced", "discounted"),
+    ("1b-fp32-long-rows", 4, 3, 2, 5, 2048, torch.float32, "mse", "equal", "discounted"),
+    ("1b-fp32-long-rows-cos", 4, 3, 2, 5, 2048, torch.float32, "cosine", "equal", "discounted"),
+    ("fp16", 4, 3, 3, 6, 512, torch.float16, "mse", "balanced", "equal"),
+    ("partial-lanes-D100", 4, 3, 3, 6, 100, torch.float32, "mse", "equal", "discounted"),
+    ("odd-D-generic", 4, 3, 3, 6, 50, torch.float32, "mse", "equal", "discounted"),
+    ("odd-D-generic-bf16-cos", 4, 3, 3, 6, 52, torch.bfloat16, "cosine", "balanced", "discounted"),
+    ("wide-5120-bf16", 3, 2, 2, 3, 5120, torch.bfloat16, "mse", "balanced", "equal"),
+]
+
+
+@pytest.mark.parametrize("vname,variant", VARIANTS)
+@pytest.mark.parametrize("shape", SHAPES, ids=[s[0] for s in SHAPES])
+@pytest.mark.parametrize("teacher", ["close", "independent"])
+def test_against_cpu_oracle(shape, teacher, vname, variant):
+    name, n_tuple, nh, B, txt, D, dtype, loss, modality, ls = shape
+    st, te, am = O.make_inputs(n_tuple, B, txt, D, n_vis=256, dtype=dtype, seed=77, teacher=teacher, mask="ragged")
+    meta = dict(modality=modality, layer_strategy=ls, loss=loss, gamma=0.5, num_hidden_layers=nh, layer=None,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    g_out = 0.25 if teacher == "independent" else 1.0
+    ref = O.forward_backward(st, te, am, oracle_cfg(meta), grad_out=g_out)
+    out = run_product(meta, st, te, am, grad_out=g_out, variant=variant)
+    logged = {f"task_0/distill_loss_{l}": float(v) for l, v in ref["layer_losses"].items()}
+    _check(out, ref["loss"], ref["grads"], dtype, logged)
+
+
+@pytest.mark.parametrize("vname,variant", VARIANTS)
+def test_edge_masks(vname, variant):
+    """All-padded rows, a fully valid mask, a single text position, and non-0/1 mask weights."""
+    st, te, am = O.make_inputs(4, 4, 6, 256, n_vis=256, seed=5, mask="full")
+    meta = dict(modality="equal", layer_strategy="equal", loss="mse", gamma=0.5, num_hidden_layers=3, layer=None,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    for mask in (am, torch.cat([torch.zeros(4, 5, dtype=torch.int64), torch.ones(4, 1, dtype=torch.int64)], 1),
+                 torch.tensor([[0] * 6, [0, 0, 1, 1, 1, 1], [1] * 6, [0] * 6]),
+                 torch.tensor([[0, 0, 2, 1, 3, 1]] * 4)):
+        ref = O.forward_backward(st, te, mask, oracle_cfg(meta))
+        out = run_product(meta, st, te, mask, variant=variant)
+        _check(out, ref["loss"], ref["grads"], torch.float32)
+    st1, te1, am1 = O.make_inputs(3, 2, 1, 64, n_vis=256, seed=6, mask="full")  # txt = 1
+    ref = O.forward_backward(st1, te1, am1, oracle_cfg(dict(meta, num_hidden_layers=2)))
+    out = run_product(dict(meta, num_hidden_layers=2), st1, te1, am1, variant=variant)
+    _check(out, ref["loss"], ref["grads"], torch.float32)
+
+
+def test_no_text_tokens_gives_nan_like_reference():
+    st, te, am = O.make_inputs(3, 2, 4, 64, n_vis=256, seed=8, mask="full")
+    am.zero_()
+    meta = dict(modality="balanced", layer_strategy="equal", loss="mse", gamma=0.5, num_hidden_layers=2, layer=None,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    ref = O.forward_backward(st, te, am, oracle_cfg(meta))
+    out = run_product(meta, st, te, am)
+    assert torch.isnan(ref["loss"]) and torch.isnan(out["loss"])
+
+
+def test_teacher_receives_no_gradient_and_unselected_layers_none():
+    st, te, am = O.make_inputs(5, 2, 4, 128, n_vis=256, seed=9)
+    meta = dict(modality="balanced", layer_strategy="single", loss="mse", gamma=0.5, num_hidden_layers=4, layer=2,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    out = run_product(meta, st, te, am)
+    assert [g is not None for g in out["grads"]] == [False, False, True, False, False]
+
+
+def test_token_loss_helpers_and_cls_api():
+    """_compute_{mse,cosine,cls}_distillation_loss keep the reference's per-call semantics."""
+    from gpu_util import make_method
+    torch.manual_seed(3)
+    h = torch.randn(3, 20, 96, device="cuda", requires_grad=True)
+    p = torch.randn(3, 20, 96, device="cuda")
+    mask = (torch.rand(3, 20, device="cuda") > 0.4).long()
+    meta = dict(modality="balanced", layer_strategy="equal", loss="mse", num_hidden_layers=2, layer=None)
+    fd = make_method(meta)
+    got = fd._compute_mse_distillation_loss(h, p, mask)
+    ref = O._mse_token_loss(h.detach().cpu(), p.cpu(), mask.cpu())
+    assert float(got) == pytest.approx(float(ref), rel=1e-5)
+    got.backward()
+    hc = h.detach().cpu().requires_grad_(True)
+    O._mse_token_loss(hc, p.cpu(), mask.cpu()).backward()
+    assert rel_err(h.grad.cpu(), hc.grad) < 1e-5
+    got = fd._compute_cosine_distillation_loss(h, p, mask)
+    assert float(got) == pytest.approx(float(O._cosine_token_loss(h.detach().cpu(), p.cpu(), mask.cpu())), rel=1e-5)
+    with pytest.raises(TypeError):
+        fd._compute_cls_distillation_loss(h, p)
+    fc = make_method(dict(meta, loss="cosine"))
+    h.grad = None
+    got = fc._compute_cls_distillation_loss(h, p)
+    hc = h.detach().cpu().requires_grad_(True)
+    ref = O._cls_loss(hc, p.cpu(), "cosine")
+    ref.backward()
+    assert float(got) == pytest.approx(float(ref), rel=1e-5)
+    got.backward()
+    assert rel_err(h.grad.cpu(), hc.grad) < 1e-5 and float(h.grad[:, 1:].abs().max()) == 0.0
+    bad = make_method(dict(meta, cls=True))
+    with pytest.raises(TypeError):
+        bad.feature_distillation({"attention_mask": mask}, h, p, 0)
+
+
+def test_feature_distillation_single_layer_call():
+    st, te, am = O.make_inputs(3, 2, 5, 64, n_vis=256, seed=11)
+    meta = dict(modality="equal", layer_strategy="discounted", loss="mse", gamma=0.5, num_hidden_layers=2, layer=None,
+                n_vis=256)
+    from gpu_util import make_method
+    fd = make_method(meta)
+    h = st[1].cuda().requires_grad_(True)
+    batch = {"attention_mask": am.cuda()}
+    got = fd.feature_distillation(batch, h, te[1].cuda(), 1)
+    cfg = oracle_cfg(dict(meta, coeff=1.0, cls=False, lang_coeff=None))
+    _, per_layer, _ = O.distill(st, te, am, cfg)
+    assert float(got) == pytest.approx(float(per_layer[1]), rel=1e-5)
+    assert "lang_masks" in batch and "image_masks" in batch
+
+
+def test_non_contiguous_and_mixed_dtype_inputs():
+    st, te, am = O.make_inputs(3, 2, 5, 64, n_vis=256, seed=12)
+    meta = dict(modality="balanced", layer_strategy="equal", loss="mse", gamma=0.5, num_hidden_layers=2, layer=None,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    ref = O.forward_backward(st, te, am, oracle_cfg(meta))
+    st_nc = [s.transpose(0, 1).contiguous().transpose(0, 1) for s in st]
+    assert not st_nc[0].is_contiguous()
+    out = run_product(meta, st_nc, te, am)
+    _check(out, ref["loss"], ref["grads"], torch.float32)
+    out = run_product(meta, st, [t.bfloat16() for t in te], am)  # teacher in another dtype: up-cast path
+    ref = O.forward_backward(st, [t.bfloat16().float() for t in te], am, oracle_cfg(meta))
+    _check(out, ref["loss"], ref["grads"], torch.float32)
+
+
+def test_sharded_partial_sums_equal_full_batch():
+    """Two batch shards reduced separately then summed (what the NCCL allreduce does) == full batch."""
+    import ctypes
+    from mafed_b200.distill_op import DistillPlan, _Launch
+    lib = cabi.load()
+    st, te, am = O.make_inputs(4, 6, 7, 256, n_vis=256, seed=13, dtype=torch.bfloat16)
+    L = 3
+    plan = DistillPlan(layers=[0, 1, 2], layer_coeffs=[0.2, 0.3, 0.5], modality_kind=cabi.MODW_EQUAL, n_vis=256)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def sums_of(lo, hi):
+        ln = _Launch([s[lo:hi].cuda().contiguous() for s in st[:L]], [t[lo:hi].cuda().contiguous() for t in te[:L]],
+                     am[lo:hi].cuda(), plan)
+        ws = torch.empty(lib.mafed_distill_ws_bytes(L), dtype=torch.uint8, device="cuda")
+        sums = torch.empty(2 * L + 2, dtype=torch.float64, device="cuda")
+        cabi.check(lib.mafed_distill_fwd(ctypes.byref(ln.shape), ln.s_ptrs, ln.t_ptrs, ln.mask_ptr, ws.data_ptr(), stream), "fwd")
+        cabi.check(lib.mafed_distill_reduce(ctypes.byref(ln.shape), ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream), "reduce")
+        torch.cuda.synchronize()
+        return sums, ln
+
+    full, ln_full = sums_of(0, 6)
+    a, _ = sums_of(0, 2)
+    b, _ = sums_of(2, 6)
+    torch.testing.assert_close(a + b, full, rtol=1e-6, atol=0)
+    assert float(full[-2]) == float(am.sum()) and float(full[-1]) == 6 * 256
+    out = torch.empty(1 + 3 * L, dtype=torch.float32, device="cuda")
+    scale = torch.empty(2 * L, dtype=torch.float32, device="cuda")
+    w = plan.weights()
+    merged = (a + b).contiguous()
+    cabi.check(lib.mafed_distill_finalize(ctypes.byref(ln_full.shape), ctypes.byref(w), merged.data_ptr(),
+                                          out.data_ptr(), scale.data_ptr(), stream), "finalize")
+    torch.cuda.synchronize()
+    cfg = O.OracleConfig(modality_strategy="equal", layer_strategy="discounted", num_hidden_layers=3,
+                         distillation_layer=None, num_vision_tokens=256)
+    # oracle with the same explicit coefficients: weight the per-layer losses by hand
+    _, per_layer, _ = O.distill([s.float() for s in st], [t.float() for t in te], am, cfg)
+    want = sum(c * float(per_layer[l]) for l, c in zip(range(3), [0.2, 0.3, 0.5]))
+    assert float(out[0]) == pytest.approx(want, rel=1e-5)

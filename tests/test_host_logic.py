@@ -1,0 +1,117 @@
+"""Host-side mirror of mafed.methods: layer plans, modality tables, API surface (not gpu)."""
+import inspect
+
+import pytest
+import torch
+
+from golden_util import load_plans
+from mafed_b200 import cabi
+from mafed_b200.methods import CLMethod, CLStrategy, DistillationWeights, FeatureDistillation, Naive
+from mafed_b200.methods.distillation_loss_weights import modality_masks
+
+
+class Opts:
+    tasks = ["a", "b", "c"]
+    batch_size = 4
+    seed = 42
+    pin_mem = False
+    accumulate_grad_batches = 4
+
+
+def test_registry_and_base_api():
+    assert CLMethod["featdistill"] is FeatureDistillation and CLMethod["naive"] is Naive
+    s = CLStrategy(opts=Opts())
+    assert (s.task_id, s.reg_lambda, s.mask, s.scaler, s.update_freq) == (0, 1.0, None, None, 4)
+    assert s.replay(model=None) == (None, 0)
+    assert [s._is_batch_after_step(i) for i in range(4)] == [False, False, False, True]
+    s.update(model=None)
+    assert s.task_id == 1
+    with pytest.raises(NotImplementedError):
+        s.compute_loss(None, 1.0)
+    assert Naive().compute_loss(None, 3.0) == 3.0 and CLStrategy().update_freq == 1
+
+
+def test_constructor_signature_matches_reference():
+    # mafed/methods/distillation.py:19-34 and distillation_loss_weights.py:10-22
+    sig = inspect.signature(FeatureDistillation.__init__)
+    names = list(sig.parameters)
+    assert names[:14] == ["self", "memory_size", "opts", "model_type", "distillation_modality_weighing_strategy",
+                          "distillation_layer_weighing_strategy", "distillation_coeff", "replay_coeff",
+                          "distillation_layer", "cls_distillation", "distillation_loss", "gamma",
+                          "num_hidden_layers", "kwargs"]
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["distillation_modality_weighing_strategy"], d["distillation_layer_weighing_strategy"]) == ("equal", "single")
+    assert (d["distillation_coeff"], d["replay_coeff"], d["distillation_layer"], d["gamma"], d["num_hidden_layers"]) == \
+        (1.0, 1.0, -1, 0.8, 11)
+    wsig = inspect.signature(DistillationWeights.__init__)
+    wd = {k: v.default for k, v in wsig.parameters.items()}
+    assert (wd["gamma"], wd["num_hidden_layers"], wd["distillation_layer"], wd["num_vision_tokens"]) == (0.9, 11, -1, 256)
+    for m in ("update", "compute_loss", "replay", "distill", "feature_distillation", "update_after_new_task",
+              "update_after_step", "update_mask", "_get_past_hidden_states", "_compute_mse_distillation_loss",
+              "_compute_cosine_distillation_loss", "_compute_cls_distillation_loss", "_update_memory", "_update_model"):
+        assert callable(getattr(FeatureDistillation, m))
+
+
+def test_layer_plans_match_reference():
+    for rec in load_plans()["plans"]:
+        kw = dict(distillation_modality_weighing_strategy="balanced",
+                  distillation_layer_weighing_strategy=rec["strategy"], gamma=rec["gamma"],
+                  num_hidden_layers=rec["num_hidden_layers"], distillation_layer=rec["layer"])
+        if "error" in rec:
+            with pytest.raises(AssertionError):
+                DistillationWeights(**kw)
+            continue
+        dw = DistillationWeights(**kw)
+        layers = dw.get_distillation_layers()
+        assert layers == rec["layers"] and dw._layer_weighing_strategy == rec["effective"]
+        assert [float(dw.get_layer_loss_weight(l)) for l in layers] == rec["coeffs"]  # bit-exact fp32
+        coeffs, kind, lang = dw.kernel_tables()
+        assert coeffs == rec["coeffs"] and kind == cabi.MODW_TABLE and lang == [0.5] * len(layers)
+
+
+def test_feature_distillation_constructor_quirks():
+    for rec in load_plans()["resolves"]:
+        kw = dict(memory_size=8, opts=Opts(), model_type="x", distillation_layer=rec["distillation_layer"],
+                  distillation_layer_weighing_strategy="equal", num_hidden_layers=rec["num_hidden_layers"])
+        if "error" in rec:
+            with pytest.raises(AssertionError):
+                FeatureDistillation(**kw)
+            continue
+        fd = FeatureDistillation(**kw)
+        assert fd.loss_weights.get_distillation_layers() == rec["layers"]
+        assert fd.memory_per_task == rec["memory_per_task"]
+    fd = FeatureDistillation(8, Opts(), "x", distillation_layer_weighing_strategy="discounted", distillation_layer=None,
+                             some_unknown_kwarg=1)
+    assert fd.update_freq == 4 and fd.num_vision_tokens == 256 and fd.step == 0 and fd.past_model is None
+    assert fd.compute_loss(None, 2.5, batch={}) == 2.5
+    with pytest.raises(AssertionError):  # CLI default: single + no layer
+        FeatureDistillation(8, Opts(), "x", distillation_layer=None)
+
+
+def test_modality_tables():
+    dw = DistillationWeights("equal", "equal", num_hidden_layers=3, distillation_layer=None)
+    assert dw.kernel_tables()[1:] == (cabi.MODW_EQUAL, None)
+    am = torch.tensor([[0, 1, 1], [1, 1, 1]])
+    lang, img = modality_masks(am, 4)
+    assert lang.tolist() == [[0, 0, 0, 0, 0, 1, 1], [0, 0, 0, 0, 1, 1, 1]] and lang.dtype == am.dtype
+    assert img.tolist() == [[1, 1, 1, 1, 0, 0, 0]] * 2
+    lw, vw = dw.get_modality_loss_weights({"lang_masks": lang, "image_masks": img}, 0)
+    assert float(lw) == pytest.approx(5 / 13) and float(vw) == pytest.approx(8 / 13)
+    ad = DistillationWeights("adaptive", "equal", num_hidden_layers=3, distillation_layer=None)
+    ad.lang_coeff = torch.tensor([0.25, 0.5, 0.75])
+    assert ad.kernel_tables([0, 2])[2] == [0.25, 0.75]
+    assert ad.get_modality_loss_weights({}, 1) == (0.5, 0.5)
+    ad.lang_coeff = torch.tensor([0.4])
+    assert ad.kernel_tables()[2] == pytest.approx([0.4] * 3)
+    with pytest.raises(NotImplementedError):
+        DistillationWeights("bogus", "equal", distillation_layer=None).get_modality_loss_weights({}, 0)
+    with pytest.raises(ValueError):
+        dw._get_dynamic_loss_weights(None)
+
+
+def test_cpu_tensors_are_refused_loudly():
+    from mafed_b200.distill_op import DistillPlan, distill_loss
+    plan = DistillPlan(layers=[0], layer_coeffs=[1.0], n_vis=2)
+    s = torch.randn(1, 3, 8, requires_grad=True)
+    with pytest.raises(cabi.MafedDistillError, match="no CPU fallback"):
+        distill_loss([s], [torch.randn(1, 3, 8)], torch.ones(1, 1, dtype=torch.int64), plan, group=False)
