@@ -5,19 +5,28 @@
  * own.  Its plug-in boundary is the Python class registry mafed/methods/__init__.py:6-11
  * (CLMethod["featdistill"] -> FeatureDistillation), mirrored by mafed_b200/methods/.  This header
  * is the boundary UNDERNEATH that mirror: plain pointers and sizes, no torch types, one entry
- * point per step of the path.  Each function cites the reference code it replaces.
+ * point per stage of the path.  Each function cites the reference code it replaces.
  *
  * Conventions
  *   - every `*_ptrs` argument is a HOST array of n_layers DEVICE pointers, one per selected layer;
- *     hidden states are separately allocated [B, T, D] tensors (vl_pythia.py:320-326), row-major,
- *     contiguous in D; consecutive token rows are `row_stride` elements apart (D when contiguous).
+ *     hidden states are separately allocated, contiguous [B, T, D] tensors (vl_pythia.py:320-326).
  *   - `attn_mask` is the DEVICE int64 [B, T - n_vis] left-padded text attention mask
  *     (data/vl_pythia_vqa_dataset.py:141-142).  Positions t <  n_vis are visual tokens with
  *     weight 1 (distillation.py:140-144); t >= n_vis are text tokens weighted by
  *     attn_mask[b, t - n_vis] (distillation.py:135-139).
  *   - `stream` is a cudaStream_t passed as void*.
  *   - return value: 0 = ok; < 0 = argument error (MAFED_E_*); > 0 = a cudaError_t.
- *   - no allocation, no host synchronisation, no global mutable state: CUDA-graph capturable.
+ *   - no allocation and no host synchronisation inside any call: every call only enqueues kernels
+ *     on `stream` and is CUDA-graph capturable.
+ *
+ * Two ways to run a step (both produce the reference's loss and gradients):
+ *   two-pass : mafed_distill_fwd -> mafed_distill_epilogue -> ... -> mafed_distill_bwd
+ *              (5*D*e bytes of HBM traffic per token*layer)
+ *   one-pass : mafed_distill_prologue -> mafed_distill_fused -> mafed_distill_epilogue(losses only)
+ *              -> ... -> mafed_distill_bwd(fix-up, returns at once when the upstream gradient is
+ *              the one assumed)                      (3*D*e bytes per token*layer)
+ * Across batch shards (one process per GPU): mafed_distill_reduce -> allreduce(sums) ->
+ * mafed_distill_finalize replace the epilogue; the one-pass step first allreduces the two counts.
  */
 #ifndef MAFED_DISTILL_H_
 #define MAFED_DISTILL_H_
@@ -29,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MAFED_ABI_VERSION 1
+#define MAFED_ABI_VERSION 2
 #define MAFED_MAX_LAYERS 64
 
 enum { MAFED_F32 = 0, MAFED_BF16 = 1, MAFED_F16 = 2 };
@@ -46,8 +55,11 @@ enum {
   MAFED_E_ARG = -1,      /* null pointer / non-positive size / too many layers */
   MAFED_E_DTYPE = -2,    /* unknown dtype or loss kind */
   MAFED_E_ALIGN = -3,    /* a pointer is not aligned to its element size */
-  MAFED_E_NODEVICE = -4  /* no CUDA device / not an sm_100 device */
+  MAFED_E_NODEVICE = -4  /* no CUDA device */
 };
+
+/* flags of mafed_distill_scalar_stage */
+enum { MAFED_STAGE_REDUCE = 1, MAFED_STAGE_COUNTS = 2, MAFED_STAGE_LOSSES = 4, MAFED_STAGE_SCALE = 8 };
 
 /* Geometry of one step.  rows of a layer: N = B*T (or B in CLS mode). */
 typedef struct mafed_shape {
@@ -72,9 +84,8 @@ typedef struct mafed_weights {
 int mafed_distill_abi_version(void);
 const char* mafed_distill_error_string(int code);
 
-/* Bytes of device workspace mafed_distill_fwd needs (per-CTA partial sums). */
+/* Bytes of device workspace mafed_distill_fwd / _fused need (per-CTA partial sums). */
 size_t mafed_distill_ws_bytes(int n_layers);
-
 /* Length (in doubles) of the `sums` vector: 2*n_layers partial sums + [n_text, n_vis]. */
 int mafed_distill_sums_len(int n_layers);
 /* Length (in floats) of the `out` vector: total, n_layers layer losses, 2*n_layers modality losses. */
@@ -86,32 +97,57 @@ int mafed_distill_out_len(int n_layers);
 int mafed_distill_fwd(const mafed_shape_t* shape, const void* const* student_ptrs,
                       const void* const* teacher_ptrs, const int64_t* attn_mask, void* ws, void* stream);
 
-/* Deterministic reduction of `ws` (fixed order, fp64) + mask counts -> sums[2L+2] on device.
- * This rank-local vector is what the single NCCL allreduce combines across batch shards. */
+/* The single-CTA scalar stage; `flags` selects its parts (MAFED_STAGE_*):
+ *   REDUCE : deterministic fp64 reduction of `ws` (fixed order) -> sums[0 .. 2L)
+ *   COUNTS : n_text = sum(attn_mask), n_vis = B*n_vis           -> sums[2L], sums[2L+1]
+ *   LOSSES : sums -> out[1+3L] = {total, layer losses, (text, vision) losses}
+ *            (distillation.py:110-120,163; distillation_loss_weights.py:148-174)
+ *   SCALE  : counts -> bwd_scale[2L] = c_l * coeff * w_m * k / n_m  (k = 2/D for mse, 1 for cosine)
+ * Parts that are not selected read their inputs from `sums`; parts that are write them there
+ * (when `sums` is not NULL).  The helpers below are the four combinations the path uses. */
+int mafed_distill_scalar_stage(const mafed_shape_t* shape, const mafed_weights_t* weights, int flags,
+                               const int64_t* attn_mask, const void* ws, double* sums, float* out,
+                               float* bwd_scale, void* stream);
+
+/* REDUCE|COUNTS: the rank-local vector the single NCCL allreduce combines across batch shards. */
 int mafed_distill_reduce(const mafed_shape_t* shape, const int64_t* attn_mask, const void* ws,
                          double* sums, void* stream);
-
-/* sums (global) -> out[1+3L] = {total, layer losses, modality losses} and the backward scale table
- * bwd_scale[2L] = c_l * coeff * w_m * k / n_m  (k = 2/D for mse, 1 for cosine).
- * Replaces distillation.py:110-120,163 and distillation_loss_weights.py:148-174. */
+/* LOSSES|SCALE from (global) sums. */
 int mafed_distill_finalize(const mafed_shape_t* shape, const mafed_weights_t* weights, const double* sums,
                            float* out, float* bwd_scale, void* stream);
-
-/* reduce + finalize in one launch (single-GPU step); `sums` (may be NULL) also receives the sums. */
+/* REDUCE|COUNTS|LOSSES|SCALE in one launch (single-GPU two-pass step); bwd_scale may be NULL
+ * (-> no SCALE, the one-pass step's epilogue). */
 int mafed_distill_epilogue(const mafed_shape_t* shape, const mafed_weights_t* weights,
                            const int64_t* attn_mask, const void* ws, double* sums, float* out,
                            float* bwd_scale, void* stream);
+/* COUNTS|SCALE before a one-pass step.  If `global_counts` is not NULL, COUNTS is skipped and
+ * global_counts[2L], [2L+1] (already allreduced) are used. */
+int mafed_distill_prologue(const mafed_shape_t* shape, const mafed_weights_t* weights,
+                           const int64_t* attn_mask, double* global_counts, double* sums, float* bwd_scale,
+                           void* stream);
 
 /* Fused backward: grad[l][row] = grad_out * bwd_scale[l][m(row)] * w(row) * d f(h,p)/dh, zero for
  * padded text rows; one pass, 2 reads + 1 write (replaces autograd's per-layer, per-modality chains
  * of distillation.py:226-249).  `grad_out` is a DEVICE float scalar (NULL = 1.0).  A NULL entry in
- * grad_ptrs skips that layer. */
+ * grad_ptrs skips that layer.  If `skip_if_equals` is not NULL (a HOST float), the launch is a
+ * fix-up after mafed_distill_fused: the kernel returns at once when *grad_out == *skip_if_equals. */
 int mafed_distill_bwd(const mafed_shape_t* shape, const void* const* student_ptrs,
                       const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
-                      const float* bwd_scale, const float* grad_out, void* stream);
+                      const float* bwd_scale, const float* grad_out, const float* skip_if_equals,
+                      void* stream);
 
-/* Experiment knob (benchmarks only): select the kernel family for the next calls.
- * 0 = default, 1 = ldg (register-staged 128-bit loads), 2 = tma (cp.async.bulk + mbarrier ring). */
+/* One-pass step: loss sums AND gradients from a single read of student and teacher.  The gradient
+ * scale depends only on the token counts and the host weight tables (not on the loss), so it is
+ * known before the pass; the upstream gradient is assumed to be `assumed_grad_out` (1/accumulate_
+ * grad_batches under Lightning, vqa_cont_learner.py:213-236) and checked later by
+ * mafed_distill_bwd(..., skip_if_equals).  A NULL entry in grad_ptrs still contributes to the sums. */
+int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_ptrs,
+                        const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
+                        const float* bwd_scale, float assumed_grad_out, void* ws, void* stream);
+
+/* Experiment knobs (benchmarks only; process-global): kernel family for the next calls
+ * (0 = default, 1 = ldg: register-staged 128-bit loads, 2 = tma: cp.async.bulk + mbarrier ring),
+ * and integer tuning keys (see mafed_b200/cabi.py). */
 int mafed_distill_set_variant(int variant);
 int mafed_distill_set_tuning(int key, int value);
 

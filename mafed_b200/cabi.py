@@ -13,16 +13,21 @@ F32, BF16, F16 = 0, 1, 2
 LOSS_MSE, LOSS_COSINE = 0, 1
 MODW_EQUAL, MODW_TABLE, MODW_CLS, MODW_TEXT_ONLY = 0, 1, 2, 3
 VARIANT_DEFAULT, VARIANT_LDG, VARIANT_TMA = 0, 1, 2
-# keys of mafed_distill_set_tuning (benchmark knobs)
-TUNE_TMA_STAGES, TUNE_TMA_ROWS, TUNE_TMA_WARPS, TUNE_LDG_BLOCKS_PER_SM, TUNE_BWD_REVERSE, TUNE_GRID_MUL = range(6)
+STAGE_REDUCE, STAGE_COUNTS, STAGE_LOSSES, STAGE_SCALE = 1, 2, 4, 8
+ABI_VERSION = 2
+# keys of mafed_distill_set_tuning (benchmark knobs); the first three are per pass: key + PASS_*
+PASS_FWD, PASS_BWD, PASS_FUSED = 0, 1, 2
+TUNE_TMA_STAGES, TUNE_TMA_ROWS, TUNE_VARIANT = 0, 3, 6
+TUNE_TMA_WARPS, TUNE_LDG_BLOCKS_PER_SM, TUNE_BWD_FORWARD_ORDER, TUNE_GRID_MUL = 9, 10, 11, 12
+N_TUNE_KEYS = 16
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmafed_distill.so")
 
 EXPORTS = (
     "mafed_distill_abi_version", "mafed_distill_error_string", "mafed_distill_ws_bytes",
-    "mafed_distill_sums_len", "mafed_distill_out_len", "mafed_distill_fwd", "mafed_distill_reduce",
-    "mafed_distill_finalize", "mafed_distill_epilogue", "mafed_distill_bwd", "mafed_distill_set_variant",
-    "mafed_distill_set_tuning",
+    "mafed_distill_sums_len", "mafed_distill_out_len", "mafed_distill_fwd", "mafed_distill_scalar_stage",
+    "mafed_distill_reduce", "mafed_distill_finalize", "mafed_distill_epilogue", "mafed_distill_prologue",
+    "mafed_distill_bwd", "mafed_distill_fused", "mafed_distill_set_variant", "mafed_distill_set_tuning",
 )
 
 
@@ -82,15 +87,21 @@ def load():
         lib.mafed_distill_finalize.argtypes = [sh, wt, vp, vp, vp, vp]
         lib.mafed_distill_epilogue.restype = i32
         lib.mafed_distill_epilogue.argtypes = [sh, wt, vp, vp, vp, vp, vp, vp]
+        lib.mafed_distill_scalar_stage.restype = i32
+        lib.mafed_distill_scalar_stage.argtypes = [sh, wt, i32, vp, vp, vp, vp, vp, vp]
+        lib.mafed_distill_prologue.restype = i32
+        lib.mafed_distill_prologue.argtypes = [sh, wt, vp, vp, vp, vp, vp]
         lib.mafed_distill_bwd.restype = i32
-        lib.mafed_distill_bwd.argtypes = [sh, pp, pp, pp, vp, vp, vp, vp]
+        lib.mafed_distill_bwd.argtypes = [sh, pp, pp, pp, vp, vp, vp, ctypes.POINTER(ctypes.c_float), vp]
+        lib.mafed_distill_fused.restype = i32
+        lib.mafed_distill_fused.argtypes = [sh, pp, pp, pp, vp, vp, ctypes.c_float, vp, vp]
         lib.mafed_distill_set_variant.restype = i32
         lib.mafed_distill_set_variant.argtypes = [i32]
         lib.mafed_distill_set_tuning.restype = i32
         lib.mafed_distill_set_tuning.argtypes = [i32, i32]
         for name in EXPORTS:
             getattr(lib, name)
-        if lib.mafed_distill_abi_version() != 1:
+        if lib.mafed_distill_abi_version() != ABI_VERSION:
             raise MafedDistillError("libmafed_distill.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

@@ -13,31 +13,30 @@
 namespace mafed {
 namespace {
 
-std::atomic<int> g_variant{0};            // 0 default, 1 ldg, 2 tma
-std::atomic<int> g_tune[8] = {};          // experiment knobs, see mafed_distill_set_tuning
+enum Pass { kPassFwd = 0, kPassBwd = 1, kPassFused = 2 };
 
-enum TuneKey { kTuneTmaStages = 0, kTuneTmaRows = 1, kTuneTmaWarps = 2, kTuneLdgBlocksPerSm = 3, kTuneBwdReverse = 4,
-               kTuneGridMul = 5 };
+std::atomic<int> g_variant{0};   // 0 default, 1 ldg, 2 tma
+std::atomic<int> g_tune[16] = {};  // experiment knobs, see mafed_distill_set_tuning
+
+// per-pass keys: base + pass (fwd, bwd, fused)
+enum TuneKey { kTuneTmaStages = 0, kTuneTmaRows = 3, kTuneVariant = 6, kTuneTmaWarps = 9, kTuneLdgBlocksPerSm = 10,
+               kTuneBwdForward = 11, kTuneGridMul = 12 };
 
 struct DeviceInfo {
   int sm_count = 0;
   int smem_optin = 0;
-  int cc_major = 0;
   bool ok = false;
 };
 
 const DeviceInfo& device_info() {
   static DeviceInfo info[16];
+  static DeviceInfo none;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) {
-    static DeviceInfo none;
-    return none;
-  }
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return none;
   DeviceInfo& d = info[dev];
   if (!d.ok) {
     cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
     d.ok = d.sm_count > 0;
   }
   return d;
@@ -72,11 +71,11 @@ void fill_geometry(const mafed_shape_t& sh, PathParams& p) {
     p.n_vis = sh.n_vis;
     p.txt = sh.T - sh.n_vis;
   }
-  p.n_chunks = 0;
-  p.reverse = 0;
 }
 
 bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+bool needs_mask(const mafed_shape_t& sh) { return !sh.cls && sh.T > sh.n_vis; }
 
 // ---------------------------------------------------------------- launch helpers
 template <typename K>
@@ -86,137 +85,169 @@ int blocks_per_sm(K kernel, int threads, size_t dyn_smem) {
   return n < 1 ? 1 : n;
 }
 
+long long clamp_grid(long long grid, long long total) {
+  if (grid > total) grid = total;
+  if (grid > kMaxPartials) grid = kMaxPartials;
+  return grid < 1 ? 1 : grid;
+}
+
 template <typename T, int CPL, int RPI, int LOSS>
-int launch_ldg(const PathParams& p, bool backward, cudaStream_t st) {
-  static int occ_f = 0, occ_b = 0;
+int launch_ldg(const PathParams& p, int pass, cudaStream_t st) {
+  static int occ[3] = {0, 0, 0};
   const DeviceInfo& dv = device_info();
-  int& occ = backward ? occ_b : occ_f;
-  if (occ == 0)
-    occ = backward ? blocks_per_sm(k_bwd_ldg<T, CPL, RPI, LOSS>, kLdgThreads, 0)
-                   : blocks_per_sm(k_fwd_ldg<T, CPL, RPI, LOSS>, kLdgThreads, 0);
-  int per_sm = occ;
+  if (occ[pass] == 0) {
+    occ[pass] = pass == kPassFwd   ? blocks_per_sm(k_fwd_ldg<T, CPL, RPI, LOSS>, kLdgThreads, 0)
+                : pass == kPassBwd ? blocks_per_sm(k_bwd_ldg<T, CPL, RPI, LOSS, kBackward>, kLdgThreads, 0)
+                                   : blocks_per_sm(k_bwd_ldg<T, CPL, RPI, LOSS, kFused>, kLdgThreads, 0);
+  }
+  int per_sm = occ[pass];
   const int cap = g_tune[kTuneLdgBlocksPerSm].load();
   if (cap > 0 && cap < per_sm) per_sm = cap;
   const long long rows_per_iter = (long long)kLdgWarps * RPI;
   const long long total = ((p.n_rows + rows_per_iter - 1) / rows_per_iter) * p.n_layers;
-  long long grid = (long long)dv.sm_count * per_sm;
-  if (grid > total) grid = total;
-  if (grid > kMaxPartials) grid = kMaxPartials;
-  if (grid < 1) grid = 1;
-  if (backward) k_bwd_ldg<T, CPL, RPI, LOSS><<<(unsigned)grid, kLdgThreads, 0, st>>>(p);
-  else k_fwd_ldg<T, CPL, RPI, LOSS><<<(unsigned)grid, kLdgThreads, 0, st>>>(p);
+  const unsigned grid = (unsigned)clamp_grid((long long)dv.sm_count * per_sm, total);
+  if (pass == kPassFwd) k_fwd_ldg<T, CPL, RPI, LOSS><<<grid, kLdgThreads, 0, st>>>(p);
+  else if (pass == kPassBwd) k_bwd_ldg<T, CPL, RPI, LOSS, kBackward><<<grid, kLdgThreads, 0, st>>>(p);
+  else k_bwd_ldg<T, CPL, RPI, LOSS, kFused><<<grid, kLdgThreads, 0, st>>>(p);
   return (int)cudaPeekAtLastError();
 }
 
 template <typename T, int LOSS>
-int dispatch_ldg(const PathParams& p, bool backward, cudaStream_t st) {
+int dispatch_ldg(const PathParams& p, int pass, cudaStream_t st) {
   const int cpl = (p.n_chunks + 31) / 32;
-  if (cpl <= 1) return launch_ldg<T, 1, 4, LOSS>(p, backward, st);
-  if (cpl <= 2) return launch_ldg<T, 2, 4, LOSS>(p, backward, st);
-  if (cpl <= 3) return launch_ldg<T, 3, 2, LOSS>(p, backward, st);
-  if (cpl <= 4) return launch_ldg<T, 4, 2, LOSS>(p, backward, st);
-  if (cpl <= 6) return launch_ldg<T, 6, 1, LOSS>(p, backward, st);
-  return launch_ldg<T, 8, 1, LOSS>(p, backward, st);  // multi-pass for rows longer than 4 KB
+  if (cpl <= 1) return launch_ldg<T, 1, 4, LOSS>(p, pass, st);
+  if (cpl <= 2) return launch_ldg<T, 2, 4, LOSS>(p, pass, st);
+  if (cpl <= 3) return launch_ldg<T, 3, 2, LOSS>(p, pass, st);
+  if (cpl <= 4) return launch_ldg<T, 4, 2, LOSS>(p, pass, st);
+  if (cpl <= 6) return launch_ldg<T, 6, 1, LOSS>(p, pass, st);
+  return launch_ldg<T, 8, 1, LOSS>(p, pass, st);  // multi-pass for rows longer than 4 KB
 }
 
+// Any D / any alignment: element-wise kernels.  The fused pass is simply forward then backward.
 template <typename T, int LOSS>
-int launch_generic(const PathParams& p, bool backward, cudaStream_t st) {
+int launch_generic(const PathParams& p, int pass, cudaStream_t st) {
   const DeviceInfo& dv = device_info();
   const long long total = ((p.n_rows + kLdgWarps - 1) / kLdgWarps) * p.n_layers;
-  long long grid = (long long)dv.sm_count * 4;
-  if (grid > total) grid = total;
-  if (grid > kMaxPartials) grid = kMaxPartials;
-  if (backward) k_bwd_generic<T, LOSS><<<(unsigned)grid, kLdgThreads, 0, st>>>(p);
-  else k_fwd_generic<T, LOSS><<<(unsigned)grid, kLdgThreads, 0, st>>>(p);
+  const unsigned grid = (unsigned)clamp_grid((long long)dv.sm_count * 4, total);
+  if (pass == kPassFwd || pass == kPassFused) k_fwd_generic<T, LOSS><<<grid, kLdgThreads, 0, st>>>(p);
+  if (pass == kPassBwd || pass == kPassFused)
+    k_bwd_generic<T, LOSS><<<grid, kLdgThreads, 0, st>>>(p, pass == kPassFused ? 1 : 0);
   return (int)cudaPeekAtLastError();
 }
 
-bool tma_geometry(const PathParams& p, TmaGeom& geo) {
+bool tma_geometry(const PathParams& p, int pass, TmaGeom& geo) {
   const DeviceInfo& dv = device_info();
   const long long row_bytes = (long long)p.n_chunks * 16;
   if (row_bytes > 32768) return false;
   const long long budget = (long long)dv.smem_optin - 16 * 1024;  // static smem + slack
-  int rows = g_tune[kTuneTmaRows].load();
+  int rows = g_tune[kTuneTmaRows + pass].load();
   if (rows <= 0) {
-    rows = (int)(65536 / (2 * row_bytes));
+    const long long stage_target = 65536;
+    rows = (int)(stage_target / (2 * row_bytes));
     if (rows >= 8) rows &= ~7;
   }
   if (rows > kTmaMaxRows) rows = kTmaMaxRows;
   if (rows < 1) rows = 1;
+  if (2 * rows * row_bytes > budget) rows = (int)(budget / (2 * row_bytes));
+  if (rows < 1) return false;
   geo.rows = rows;
   geo.stage_bytes = (int)(2 * rows * row_bytes);
-  int stages = g_tune[kTuneTmaStages].load();
+  int stages = g_tune[kTuneTmaStages + pass].load();
   if (stages <= 0) stages = 4;
-  while (stages > 1 && (long long)stages * geo.stage_bytes > budget) --stages;
   if (stages > kTmaMaxStages) stages = kTmaMaxStages;
-  if ((long long)stages * geo.stage_bytes > budget) return false;
+  while (stages > 1 && (long long)stages * geo.stage_bytes > budget) --stages;
   geo.stages = stages;
   return true;
 }
 
 template <typename T, int LOSS, int NCW>
-int launch_tma(const PathParams& p, const TmaGeom& geo, bool backward, cudaStream_t st) {
-  static bool attr_f = false, attr_b = false;
+int launch_tma(const PathParams& p, const TmaGeom& geo, int pass, cudaStream_t st) {
+  static bool attr[3] = {false, false, false};
   const DeviceInfo& dv = device_info();
   const size_t dyn = (size_t)geo.stages * geo.stage_bytes;
-  bool& attr = backward ? attr_b : attr_f;
-  if (!attr) {
-    cudaError_t e = backward
-        ? cudaFuncSetAttribute(k_bwd_tma<T, LOSS, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, dv.smem_optin - 16 * 1024)
-        : cudaFuncSetAttribute(k_fwd_tma<T, LOSS, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, dv.smem_optin - 16 * 1024);
+  const int max_dyn = dv.smem_optin - 16 * 1024;
+  if (!attr[pass]) {
+    cudaError_t e =
+        pass == kPassFwd ? cudaFuncSetAttribute(k_fwd_tma<T, LOSS, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn)
+        : pass == kPassBwd
+            ? cudaFuncSetAttribute(k_bwd_tma<T, LOSS, NCW, kBackward>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn)
+            : cudaFuncSetAttribute(k_bwd_tma<T, LOSS, NCW, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     if (e != cudaSuccess) return (int)e;
-    attr = true;
+    attr[pass] = true;
   }
   const long long total = ((p.n_rows + geo.rows - 1) / geo.rows) * p.n_layers;
   int mul = g_tune[kTuneGridMul].load();
   if (mul <= 0) mul = 1;
-  long long grid = (long long)dv.sm_count * mul;
-  if (grid > total) grid = total;
-  if (grid > kMaxPartials) grid = kMaxPartials;
+  const unsigned grid = (unsigned)clamp_grid((long long)dv.sm_count * mul, total);
   constexpr int threads = (NCW + 1) * 32;
-  if (backward) k_bwd_tma<T, LOSS, NCW><<<(unsigned)grid, threads, dyn, st>>>(p, geo);
-  else k_fwd_tma<T, LOSS, NCW><<<(unsigned)grid, threads, dyn, st>>>(p, geo);
+  if (pass == kPassFwd) k_fwd_tma<T, LOSS, NCW><<<grid, threads, dyn, st>>>(p, geo);
+  else if (pass == kPassBwd) k_bwd_tma<T, LOSS, NCW, kBackward><<<grid, threads, dyn, st>>>(p, geo);
+  else k_bwd_tma<T, LOSS, NCW, kFused><<<grid, threads, dyn, st>>>(p, geo);
   return (int)cudaPeekAtLastError();
 }
 
 template <typename T, int LOSS>
-int dispatch_typed(PathParams& p, bool vector_ok, bool backward, cudaStream_t st) {
-  if (!vector_ok) return launch_generic<T, LOSS>(p, backward, st);
-  int variant = g_variant.load();
+int dispatch_typed(PathParams& p, bool vector_ok, int pass, cudaStream_t st) {
+  if (!vector_ok) return launch_generic<T, LOSS>(p, pass, st);
+  int variant = g_tune[kTuneVariant + pass].load();
+  if (variant == 0) variant = g_variant.load();
   if (variant == 0) variant = 2;
   if (variant == 2) {
     TmaGeom geo;
-    if (tma_geometry(p, geo)) {
-      if (g_tune[kTuneTmaWarps].load() == 16) return launch_tma<T, LOSS, 16>(p, geo, backward, st);
-      return launch_tma<T, LOSS, 8>(p, geo, backward, st);
+    if (tma_geometry(p, pass, geo)) {
+      if (g_tune[kTuneTmaWarps].load() == 16) return launch_tma<T, LOSS, 16>(p, geo, pass, st);
+      return launch_tma<T, LOSS, 8>(p, geo, pass, st);
     }
   }
-  return dispatch_ldg<T, LOSS>(p, backward, st);
+  return dispatch_ldg<T, LOSS>(p, pass, st);
 }
 
 template <typename T>
-int dispatch_loss(PathParams& p, int loss, bool vector_ok, bool backward, cudaStream_t st) {
-  if (loss == MAFED_LOSS_MSE) return dispatch_typed<T, MAFED_LOSS_MSE>(p, vector_ok, backward, st);
-  return dispatch_typed<T, MAFED_LOSS_COSINE>(p, vector_ok, backward, st);
+int dispatch_loss(PathParams& p, int loss, bool vector_ok, int pass, cudaStream_t st) {
+  if (loss == MAFED_LOSS_MSE) return dispatch_typed<T, MAFED_LOSS_MSE>(p, vector_ok, pass, st);
+  return dispatch_typed<T, MAFED_LOSS_COSINE>(p, vector_ok, pass, st);
 }
 
-int dispatch(const mafed_shape_t& sh, PathParams& p, bool backward, cudaStream_t st) {
+int dispatch(const mafed_shape_t& sh, PathParams& p, int pass, cudaStream_t st) {
   // vector path: rows are whole, 16-byte aligned chunks
   const size_t es = elem_size(sh.dtype);
   bool vector_ok = ((size_t)sh.D * es) % 16 == 0 && ((size_t)p.row_stride * es) % 16 == 0;
-  for (int l = 0; l < sh.n_layers && vector_ok; ++l) {
-    vector_ok = aligned_to(p.s[l], 16) && aligned_to(p.t[l], 16) && (!backward || aligned_to(p.g[l], 16));
-  }
+  for (int l = 0; l < sh.n_layers && vector_ok; ++l)
+    vector_ok = aligned_to(p.s[l], 16) && aligned_to(p.t[l], 16) && (pass == kPassFwd || aligned_to(p.g[l], 16));
   p.n_chunks = vector_ok ? (int)((size_t)sh.D * es / 16) : 0;
   switch (sh.dtype) {
-    case MAFED_F32: return dispatch_loss<float>(p, sh.loss_kind, vector_ok, backward, st);
-    case MAFED_BF16: return dispatch_loss<__nv_bfloat16>(p, sh.loss_kind, vector_ok, backward, st);
-    default: return dispatch_loss<__half>(p, sh.loss_kind, vector_ok, backward, st);
+    case MAFED_F32: return dispatch_loss<float>(p, sh.loss_kind, vector_ok, pass, st);
+    case MAFED_BF16: return dispatch_loss<__nv_bfloat16>(p, sh.loss_kind, vector_ok, pass, st);
+    default: return dispatch_loss<__half>(p, sh.loss_kind, vector_ok, pass, st);
   }
 }
 
-int launch_epilogue(const mafed_shape_t& sh, const mafed_weights_t* w, const int64_t* mask, const void* ws,
-                    double* sums, float* out, float* bwd_scale, bool do_reduce, bool do_finalize, cudaStream_t st) {
+// Common argument checks + pointer-table copy for the three streaming passes.
+int fill_params(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
+                void* const* grad_ptrs, const int64_t* attn_mask, PathParams& p) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!student_ptrs || !teacher_ptrs || (needs_mask(*shape) && !attn_mask)) return MAFED_E_ARG;
+  if (!device_info().ok) return MAFED_E_NODEVICE;
+  memset(&p, 0, sizeof(p));
+  fill_geometry(*shape, p);
+  const size_t es = elem_size(shape->dtype);
+  for (int l = 0; l < shape->n_layers; ++l) {
+    if (!student_ptrs[l] || !teacher_ptrs[l]) return MAFED_E_ARG;
+    if (!aligned_to(student_ptrs[l], es) || !aligned_to(teacher_ptrs[l], es)) return MAFED_E_ALIGN;
+    p.s[l] = student_ptrs[l];
+    p.t[l] = teacher_ptrs[l];
+    if (grad_ptrs) {
+      if (!aligned_to(grad_ptrs[l], es)) return MAFED_E_ALIGN;
+      p.g[l] = grad_ptrs[l];
+    }
+  }
+  p.mask = attn_mask;
+  return 0;
+}
+
+int launch_scalar_stage(const mafed_shape_t& sh, const mafed_weights_t* w, int flags, const int64_t* mask,
+                        const void* ws, double* sums, float* out, float* bwd_scale, cudaStream_t st) {
   EpiParams e;
   memset(&e, 0, sizeof(e));
   e.ws = reinterpret_cast<const float*>(ws);
@@ -224,13 +255,12 @@ int launch_epilogue(const mafed_shape_t& sh, const mafed_weights_t* w, const int
   e.sums = sums;
   e.out = out;
   e.bwd_scale = bwd_scale;
-  e.n_mask = sh.cls ? 0 : (long long)sh.B * (sh.T - sh.n_vis);
+  e.n_mask = needs_mask(sh) ? (long long)sh.B * (sh.T - sh.n_vis) : 0;
   e.n_vis_rows = sh.cls ? (double)sh.B : (double)sh.B * (double)sh.n_vis;
   e.n_layers = sh.n_layers;
   e.D = sh.D;
   e.loss_kind = sh.loss_kind;
-  e.do_reduce = do_reduce;
-  e.do_finalize = do_finalize;
+  e.flags = flags;
   if (w != nullptr) e.w = *w;
   k_epilogue<<<1, kEpiThreads, 0, st>>>(e);
   return (int)cudaPeekAtLastError();
@@ -267,75 +297,86 @@ int mafed_distill_out_len(int n_layers) { return 1 + 3 * n_layers; }
 
 int mafed_distill_fwd(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
                       const int64_t* attn_mask, void* ws, void* stream) {
+  PathParams p;
+  int rc = fill_params(shape, student_ptrs, teacher_ptrs, nullptr, attn_mask, p);
+  if (rc) return rc;
+  if (!ws) return MAFED_E_ARG;
+  p.ws = reinterpret_cast<float*>(ws);
+  return dispatch(*shape, p, kPassFwd, (cudaStream_t)stream);
+}
+
+int mafed_distill_scalar_stage(const mafed_shape_t* shape, const mafed_weights_t* weights, int flags,
+                               const int64_t* attn_mask, const void* ws, double* sums, float* out, float* bwd_scale,
+                               void* stream) {
   int rc = check_shape(shape);
   if (rc) return rc;
-  if (!student_ptrs || !teacher_ptrs || !ws || (!shape->cls && shape->T > shape->n_vis && !attn_mask)) return MAFED_E_ARG;
-  if (!device_info().ok) return MAFED_E_NODEVICE;
-  PathParams p;
-  memset(&p, 0, sizeof(p));
-  fill_geometry(*shape, p);
-  const size_t es = elem_size(shape->dtype);
-  for (int l = 0; l < shape->n_layers; ++l) {
-    if (!student_ptrs[l] || !teacher_ptrs[l]) return MAFED_E_ARG;
-    if (!aligned_to(student_ptrs[l], es) || !aligned_to(teacher_ptrs[l], es)) return MAFED_E_ALIGN;
-    p.s[l] = student_ptrs[l];
-    p.t[l] = teacher_ptrs[l];
-  }
-  p.mask = attn_mask;
-  p.ws = reinterpret_cast<float*>(ws);
-  return dispatch(*shape, p, false, (cudaStream_t)stream);
+  if ((flags & MAFED_STAGE_REDUCE) && !ws) return MAFED_E_ARG;
+  if ((flags & MAFED_STAGE_COUNTS) && needs_mask(*shape) && !attn_mask) return MAFED_E_ARG;
+  if ((flags & (MAFED_STAGE_LOSSES | MAFED_STAGE_SCALE)) && !weights) return MAFED_E_ARG;
+  if ((flags & MAFED_STAGE_LOSSES) && !out) return MAFED_E_ARG;
+  if ((flags & MAFED_STAGE_SCALE) && !bwd_scale) return MAFED_E_ARG;
+  const bool reads_sums = ((flags & MAFED_STAGE_LOSSES) && !(flags & MAFED_STAGE_REDUCE)) ||
+                          ((flags & (MAFED_STAGE_LOSSES | MAFED_STAGE_SCALE)) && !(flags & MAFED_STAGE_COUNTS));
+  const bool only_writes = (flags & (MAFED_STAGE_LOSSES | MAFED_STAGE_SCALE)) == 0;
+  if ((reads_sums || only_writes) && !sums) return MAFED_E_ARG;
+  return launch_scalar_stage(*shape, weights, flags, attn_mask, ws, sums, out, bwd_scale, (cudaStream_t)stream);
 }
 
 int mafed_distill_reduce(const mafed_shape_t* shape, const int64_t* attn_mask, const void* ws, double* sums,
                          void* stream) {
-  int rc = check_shape(shape);
-  if (rc) return rc;
-  if (!ws || !sums) return MAFED_E_ARG;
-  return launch_epilogue(*shape, nullptr, attn_mask, ws, sums, nullptr, nullptr, true, false, (cudaStream_t)stream);
+  return mafed_distill_scalar_stage(shape, nullptr, MAFED_STAGE_REDUCE | MAFED_STAGE_COUNTS, attn_mask, ws, sums,
+                                    nullptr, nullptr, stream);
 }
 
 int mafed_distill_finalize(const mafed_shape_t* shape, const mafed_weights_t* weights, const double* sums, float* out,
                            float* bwd_scale, void* stream) {
-  int rc = check_shape(shape);
-  if (rc) return rc;
-  if (!weights || !sums || !out || !bwd_scale) return MAFED_E_ARG;
-  return launch_epilogue(*shape, weights, nullptr, nullptr, const_cast<double*>(sums), out, bwd_scale, false, true,
-                         (cudaStream_t)stream);
+  return mafed_distill_scalar_stage(shape, weights, MAFED_STAGE_LOSSES | (bwd_scale ? MAFED_STAGE_SCALE : 0), nullptr,
+                                    nullptr, const_cast<double*>(sums), out, bwd_scale, stream);
 }
 
 int mafed_distill_epilogue(const mafed_shape_t* shape, const mafed_weights_t* weights, const int64_t* attn_mask,
                            const void* ws, double* sums, float* out, float* bwd_scale, void* stream) {
-  int rc = check_shape(shape);
-  if (rc) return rc;
-  if (!weights || !ws || !out || !bwd_scale) return MAFED_E_ARG;
-  return launch_epilogue(*shape, weights, attn_mask, ws, sums, out, bwd_scale, true, true, (cudaStream_t)stream);
+  const int flags = MAFED_STAGE_REDUCE | MAFED_STAGE_COUNTS | MAFED_STAGE_LOSSES | (bwd_scale ? MAFED_STAGE_SCALE : 0);
+  return mafed_distill_scalar_stage(shape, weights, flags, attn_mask, ws, sums, out, bwd_scale, stream);
+}
+
+int mafed_distill_prologue(const mafed_shape_t* shape, const mafed_weights_t* weights, const int64_t* attn_mask,
+                           double* global_counts, double* sums, float* bwd_scale, void* stream) {
+  if (global_counts != nullptr)
+    return mafed_distill_scalar_stage(shape, weights, MAFED_STAGE_SCALE, nullptr, nullptr, global_counts, nullptr,
+                                      bwd_scale, stream);
+  return mafed_distill_scalar_stage(shape, weights, MAFED_STAGE_COUNTS | MAFED_STAGE_SCALE, attn_mask, nullptr, sums,
+                                    nullptr, bwd_scale, stream);
 }
 
 int mafed_distill_bwd(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
                       void* const* grad_ptrs, const int64_t* attn_mask, const float* bwd_scale, const float* grad_out,
-                      void* stream) {
-  int rc = check_shape(shape);
-  if (rc) return rc;
-  if (!student_ptrs || !teacher_ptrs || !grad_ptrs || !bwd_scale) return MAFED_E_ARG;
-  if (!shape->cls && shape->T > shape->n_vis && !attn_mask) return MAFED_E_ARG;
-  if (!device_info().ok) return MAFED_E_NODEVICE;
+                      const float* skip_if_equals, void* stream) {
+  if (!grad_ptrs || !bwd_scale) return MAFED_E_ARG;
   PathParams p;
-  memset(&p, 0, sizeof(p));
-  fill_geometry(*shape, p);
-  const size_t es = elem_size(shape->dtype);
-  for (int l = 0; l < shape->n_layers; ++l) {
-    if (!student_ptrs[l] || !teacher_ptrs[l]) return MAFED_E_ARG;
-    if (!aligned_to(student_ptrs[l], es) || !aligned_to(teacher_ptrs[l], es) || !aligned_to(grad_ptrs[l], es))
-      return MAFED_E_ALIGN;
-    p.s[l] = student_ptrs[l];
-    p.t[l] = teacher_ptrs[l];
-    p.g[l] = grad_ptrs[l];
-  }
-  p.mask = attn_mask;
+  int rc = fill_params(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, p);
+  if (rc) return rc;
   p.bwd_scale = bwd_scale;
   p.grad_out = grad_out;
-  p.reverse = g_tune[kTuneBwdReverse].load() == 2 ? 0 : 1;
-  return dispatch(*shape, p, true, (cudaStream_t)stream);
+  if (skip_if_equals != nullptr) {
+    p.skip_if_gout_equals = 1;
+    p.fixed_gout = *skip_if_equals;
+  }
+  p.reverse = g_tune[kTuneBwdForward].load() ? 0 : 1;
+  return dispatch(*shape, p, kPassBwd, (cudaStream_t)stream);
+}
+
+int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
+                        void* const* grad_ptrs, const int64_t* attn_mask, const float* bwd_scale, float assumed_grad_out,
+                        void* ws, void* stream) {
+  if (!grad_ptrs || !bwd_scale || !ws) return MAFED_E_ARG;
+  PathParams p;
+  int rc = fill_params(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, p);
+  if (rc) return rc;
+  p.bwd_scale = bwd_scale;
+  p.fixed_gout = assumed_grad_out;
+  p.ws = reinterpret_cast<float*>(ws);
+  return dispatch(*shape, p, kPassFused, (cudaStream_t)stream);
 }
 
 int mafed_distill_set_variant(int variant) {
@@ -345,7 +386,7 @@ int mafed_distill_set_variant(int variant) {
 }
 
 int mafed_distill_set_tuning(int key, int value) {
-  if (key < 0 || key >= 8) return MAFED_E_ARG;
+  if (key < 0 || key >= 16) return MAFED_E_ARG;
   g_tune[key].store(value);
   return 0;
 }

@@ -32,7 +32,13 @@ struct PathParams {
   int D;
   int n_chunks;                  // 16-byte chunks per row (vector kernels)
   int reverse;                   // backward: walk work items last-to-first (L2 reuse after forward)
+  float fixed_gout;              // fused pass: upstream gradient assumed at forward time (host value)
+  int skip_if_gout_equals;       // backward fix-up: return at once when *grad_out == fixed_gout
 };
+
+// What a "backward-shaped" kernel does: kBackward writes gradients only; kFused also accumulates
+// the loss sums in the same pass over student and teacher (3*D*e bytes per token*layer instead of 5).
+enum PassMode { kBackward = 1, kFused = 2 };
 
 // ---------------------------------------------------------------- element packing (16-byte vectors)
 template <typename T> struct Pack;

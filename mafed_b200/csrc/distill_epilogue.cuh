@@ -1,5 +1,10 @@
-// Single-CTA epilogue: deterministic fp64 reduction of the per-CTA partial sums, mask counts, and
-// the scalar loss algebra of distillation.py:110-120,163 / distillation_loss_weights.py:148-174.
+// Single-CTA scalar stage: deterministic fp64 reduction of the per-CTA partial sums, mask counts, the
+// loss algebra of distillation.py:110-120,163 / distillation_loss_weights.py:148-174 and the
+// backward scale table.  Which parts run is a set of flags so the same kernel serves as
+//   epilogue  (reduce + counts + losses + scale)     single GPU, two-pass step
+//   reduce    (reduce + counts)                      before the allreduce
+//   finalize  (losses + scale from given sums)       after the allreduce
+//   prologue  (counts + scale)                       before a fused single-pass step
 #pragma once
 #include "distill_common.cuh"
 
@@ -7,19 +12,20 @@ namespace mafed {
 
 constexpr int kEpiThreads = 1024;
 
+enum EpiFlags { kEpiReduce = 1, kEpiCounts = 2, kEpiLosses = 4, kEpiScale = 8 };
+
 struct EpiParams {
-  const float* ws;        // partial sums (reduce phase)
-  const int64_t* mask;    // [B, txt]
-  double* sums;           // [2L + 2]: in (finalize only) / out (reduce)
-  float* out;             // [1 + 3L]
-  float* bwd_scale;       // [2L]
+  const float* ws;        // partial sums (kEpiReduce)
+  const int64_t* mask;    // [B, txt] (kEpiCounts)
+  double* sums;           // [2L + 2]: read when a part is not computed here, written when it is
+  float* out;             // [1 + 3L] (kEpiLosses)
+  float* bwd_scale;       // [2L] (kEpiScale)
   long long n_mask;       // B * txt
   double n_vis_rows;      // B * n_vis (or B in cls mode)
   int n_layers;
   int D;
   int loss_kind;
-  int do_reduce;
-  int do_finalize;
+  int flags;
   mafed_weights_t w;
 };
 
@@ -30,7 +36,7 @@ __global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.n_layers;
 
-  if (p.do_reduce) {
+  if (p.flags & kEpiReduce) {
     const int n_part = reinterpret_cast<const int*>(p.ws)[0];
     const float* part = p.ws + kWsHeaderFloats;
     // one warp per (layer, modality) pair; lanes stride over the CTA partials in a fixed order
@@ -40,6 +46,10 @@ __global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant_
       acc = warp_sum(acc);
       if (lane == 0) s_sums[pair] = acc;
     }
+  } else if (p.flags & kEpiLosses) {
+    for (int i = threadIdx.x; i < 2 * L; i += kEpiThreads) s_sums[i] = p.sums[i];
+  }
+  if (p.flags & kEpiCounts) {
     // text-token count = sum of the attention mask (distillation.py:248 `mask.sum()`)
     long long c = 0;
     for (long long i = threadIdx.x; i < p.n_mask; i += kEpiThreads) c += p.mask[i];
@@ -53,17 +63,22 @@ __global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant_
       s_sums[2 * L] = (double)tot;
       s_sums[2 * L + 1] = p.n_vis_rows;
     }
-    __syncthreads();
-    if (p.sums != nullptr)
-      for (int i = threadIdx.x; i < 2 * L + 2; i += kEpiThreads) p.sums[i] = s_sums[i];
-  } else {
-    for (int i = threadIdx.x; i < 2 * L + 2; i += kEpiThreads) s_sums[i] = p.sums[i];
-    __syncthreads();
+  } else if (threadIdx.x < 2) {
+    s_sums[2 * L + threadIdx.x] = p.sums[2 * L + threadIdx.x];
   }
-  if (!p.do_finalize) return;
+  __syncthreads();
+  if (p.sums != nullptr) {
+    if (p.flags & kEpiReduce)
+      for (int i = threadIdx.x; i < 2 * L; i += kEpiThreads) p.sums[i] = s_sums[i];
+    if ((p.flags & kEpiCounts) && threadIdx.x < 2) p.sums[2 * L + threadIdx.x] = s_sums[2 * L + threadIdx.x];
+  }
+  if (!(p.flags & (kEpiLosses | kEpiScale))) return;
 
+  const bool want_loss = p.flags & kEpiLosses, want_scale = p.flags & kEpiScale;
   const double n_text = s_sums[2 * L], n_vis = s_sums[2 * L + 1];
   const double k = (p.loss_kind == MAFED_LOSS_MSE) ? 1.0 / (double)p.D : 1.0;
+  const bool cls = p.w.modality_kind == MAFED_MODW_CLS;
+  const bool text_only = p.w.modality_kind == MAFED_MODW_TEXT_ONLY;
   for (int l = threadIdx.x; l < L; l += kEpiThreads) {
     double wt, wv;
     if (p.w.modality_kind == MAFED_MODW_EQUAL) {
@@ -72,27 +87,30 @@ __global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant_
     } else if (p.w.modality_kind == MAFED_MODW_TABLE) {
       wt = (double)p.w.lang_weight[l];
       wv = (double)(float)(1.0 - wt);
-    } else if (p.w.modality_kind == MAFED_MODW_TEXT_ONLY) {
+    } else if (text_only) {
       wt = 1.0;
       wv = 0.0;
     } else {  // CLS: vision slot only
       wt = 0.0;
       wv = 1.0;
     }
-    const bool cls = p.w.modality_kind == MAFED_MODW_CLS;
-    const bool text_only = p.w.modality_kind == MAFED_MODW_TEXT_ONLY;
-    const double text_loss = cls ? 0.0 : s_sums[2 * l] * k / n_text;  // 0/0 -> NaN, as in the reference
-    const double vis_loss = text_only ? 0.0 : s_sums[2 * l + 1] * k / n_vis;
-    const double layer_loss = cls ? vis_loss : (text_only ? text_loss : wt * text_loss + wv * vis_loss);
     const double c = (double)p.w.layer_coeff[l] * (double)p.w.distill_coeff;
-    s_layer[l] = c * layer_loss;
-    p.out[1 + l] = (float)layer_loss;
-    p.out[1 + L + 2 * l] = (float)text_loss;
-    p.out[1 + L + 2 * l + 1] = (float)vis_loss;
-    const double g = (p.loss_kind == MAFED_LOSS_MSE) ? 2.0 * k : 1.0;
-    p.bwd_scale[2 * l] = cls ? 0.f : (float)(c * wt * g / n_text);
-    p.bwd_scale[2 * l + 1] = text_only ? 0.f : (float)(c * wv * g / n_vis);
+    if (want_loss) {
+      const double text_loss = cls ? 0.0 : s_sums[2 * l] * k / n_text;  // 0/0 -> NaN, as in the reference
+      const double vis_loss = text_only ? 0.0 : s_sums[2 * l + 1] * k / n_vis;
+      const double layer_loss = cls ? vis_loss : (text_only ? text_loss : wt * text_loss + wv * vis_loss);
+      s_layer[l] = c * layer_loss;
+      p.out[1 + l] = (float)layer_loss;
+      p.out[1 + L + 2 * l] = (float)text_loss;
+      p.out[1 + L + 2 * l + 1] = (float)vis_loss;
+    }
+    if (want_scale) {
+      const double g = (p.loss_kind == MAFED_LOSS_MSE) ? 2.0 * k : 1.0;
+      p.bwd_scale[2 * l] = cls ? 0.f : (float)(c * wt * g / n_text);
+      p.bwd_scale[2 * l + 1] = text_only ? 0.f : (float)(c * wv * g / n_vis);
+    }
   }
+  if (!want_loss) return;
   __syncthreads();
   if (threadIdx.x == 0) {
     double tot = 0.0;

@@ -225,23 +225,36 @@ __device__ __forceinline__ void grad_elems_tma(const float (&a)[NE], const float
   }
 }
 
-template <typename T, int LOSS, int NCW>
+// MODE = kBackward: gradients only.  MODE = kFused: the consumers also accumulate the forward's loss
+// sums from the rows they already hold in shared memory (one pass over student and teacher per step).
+template <typename T, int LOSS, int NCW, int MODE>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1)
 k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom geo) {
   constexpr int NE = Pack<T>::kPer16;
+  constexpr bool FUSED = MODE == kFused;
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ TmaSmem sm;
+  __shared__ CtaSums<FUSED ? NCW : 1> sums;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gout;
+  if (FUSED) {
+    gout = p.fixed_gout;
+  } else {
+    gout = p.grad_out ? __ldg(p.grad_out) : 1.f;
+    if (p.skip_if_gout_equals && gout == p.fixed_gout) return;  // fix-up launch with nothing to fix
+  }
+  if (FUSED) cta_sums_zero(sums, p.n_layers);
   tma_prologue<NCW>(sm, geo);
   if (warp == NCW) {
-    tma_producer<T>(p, geo, dyn_smem, sm.full, sm.empty, sm.meta, lane, true);
+    tma_producer<T>(p, geo, dyn_smem, sm.full, sm.empty, sm.meta, lane, !FUSED);
     return;
   }
   const long long tiles_per_layer = (p.n_rows + geo.rows - 1) / geo.rows;
   const long long total = tiles_per_layer * p.n_layers;
   const uint32_t row_bytes = (uint32_t)p.n_chunks * 16u;
   const long long row_pitch = p.row_stride * (long long)sizeof(T);
-  const float gout = p.grad_out ? __ldg(p.grad_out) : 1.f;
+  float acc_text = 0.f, acc_vis = 0.f;
+  int cur = -1;
   int stage = 0;
   uint32_t phase = 0;
   long long it = 0;
@@ -249,24 +262,30 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
     mbar_wait(smem_u32(&sm.full[stage]), phase);
     const TmaStageMeta& mt = sm.meta[stage];
     const int l = mt.layer;
+    if (FUSED && l != cur) {
+      cta_sums_flush(sums, warp, lane, cur, acc_text, acc_vis);
+      acc_text = acc_vis = 0.f;
+      cur = l;
+    }
     char* gb = reinterpret_cast<char*>(p.g[l]);
     const uint32_t s_base = smem_u32(dyn_smem + (size_t)stage * geo.stage_bytes);
     const uint32_t t_base = s_base + (uint32_t)geo.rows * row_bytes;
     const int first = (int)((warp + NCW - (int)((it * geo.rows) % NCW)) % NCW);
-    if (gb != nullptr) {
+    if (FUSED || gb != nullptr) {
       for (int r = first; r < mt.n_rows; r += NCW) {
         char* grow = gb + (mt.row0 + r) * row_pitch;
-        const float w = mt.w[r] * gout * __ldg(p.bwd_scale + 2 * l + mt.mod[r]);
+        const float w = mt.w[r] * (gout * __ldg(p.bwd_scale + 2 * l + mt.mod[r]));
         if (mt.w[r] == 0.f) {  // padded text row: nothing was fetched; grad = 0 * scale (zero, or NaN if scale is)
           float o[NE];
 #pragma unroll
           for (int i = 0; i < NE; ++i) o[i] = w;
           const uint4 fill = Pack<T>::pack(o);
-          for (int c = lane; c < p.n_chunks; c += 32) stg_128(grow + (long long)c * 16, fill);
+          if (gb != nullptr)
+            for (int c = lane; c < p.n_chunks; c += 32) stg_128(grow + (long long)c * 16, fill);
           continue;
         }
         const uint32_t sa = s_base + (uint32_t)r * row_bytes, ta = t_base + (uint32_t)r * row_bytes;
-        float ch = 0.f, cp = 0.f;
+        float ch = 0.f, cp = 0.f, rowval = 0.f;
         if (LOSS == MAFED_LOSS_COSINE) {
           float x = 0.f, y = 0.f, z = 0.f;
           for (int c = lane; c < p.n_chunks; c += 32) {
@@ -279,6 +298,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
           const float aa = y + kCosEps, den = sqrtf(aa * (z + kCosEps));
           ch = w * (x / den) / aa;
           cp = w / den;
+          rowval = (lane == 0) ? 1.f - x / den : 0.f;
         }
         int c = lane;
         for (; c + 96 < p.n_chunks; c += 128) {
@@ -293,22 +313,39 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
             float a[NE], b[NE], o[NE];
             Pack<T>::unpack(sv[u], a);
             Pack<T>::unpack(tv[u], b);
+            if (FUSED && LOSS == MAFED_LOSS_MSE) {
+              float y = 0.f, z = 0.f;
+              accumulate<LOSS, NE>(a, b, rowval, y, z);
+            }
             grad_elems_tma<LOSS, NE>(a, b, w, ch, cp, o);
-            stg_128(grow + (long long)(c + 32 * u) * 16, Pack<T>::pack(o));
+            if (gb != nullptr) stg_128(grow + (long long)(c + 32 * u) * 16, Pack<T>::pack(o));
           }
         }
         for (; c < p.n_chunks; c += 32) {
           float a[NE], b[NE], o[NE];
           Pack<T>::unpack(lds_128(sa + (uint32_t)c * 16u), a);
           Pack<T>::unpack(lds_128(ta + (uint32_t)c * 16u), b);
+          if (FUSED && LOSS == MAFED_LOSS_MSE) {
+            float y = 0.f, z = 0.f;
+            accumulate<LOSS, NE>(a, b, rowval, y, z);
+          }
           grad_elems_tma<LOSS, NE>(a, b, w, ch, cp, o);
-          stg_128(grow + (long long)c * 16, Pack<T>::pack(o));
+          if (gb != nullptr) stg_128(grow + (long long)c * 16, Pack<T>::pack(o));
+        }
+        if (FUSED) {
+          if (mt.mod[r] == 0) acc_text = fmaf(mt.w[r], rowval, acc_text);
+          else acc_vis = fmaf(mt.w[r], rowval, acc_vis);
         }
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stage]));
     if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
+  }
+  if (FUSED) {
+    cta_sums_flush(sums, warp, lane, cur, acc_text, acc_vis);
+    named_bar_sync(1, NCW * 32);
+    cta_sums_store(sums, p.ws, p.n_layers, 0, NCW * 32);
   }
 }
 

@@ -1,15 +1,25 @@
 """The fused distillation operator: host tables -> C ABI -> sm_100a kernels, with autograd.
 
-One step = one fused forward launch over all selected layers (+ a single-CTA epilogue), one fused
-backward launch.  Under ``torch.distributed`` with batch sharding, the per-rank ``[2L+2]`` partial
-sums are combined by a single allreduce between the forward and the epilogue; the backward needs no
-collective.  Nothing here synchronises the host with the device.
+Two ways to run a step, same results:
+
+* two-pass  -- fused forward over all selected layers (+ a single-CTA epilogue), later one fused
+  backward: 5*D*e bytes of HBM traffic per token*layer;
+* one-pass  -- the gradient scale depends only on the token counts and the host weight tables, not
+  on the loss, so one kernel produces the loss sums AND the gradients from a single read of student
+  and teacher (3*D*e bytes).  The upstream gradient is assumed (``plan.assumed_grad_out``, i.e.
+  ``1 / accumulate_grad_batches`` under Lightning); ``backward`` launches a fix-up that returns at
+  once when the real upstream gradient equals the assumed one and otherwise recomputes exactly.
+
+Under ``torch.distributed`` with batch sharding, the per-rank ``[2L+2]`` fp64 partial sums / counts
+are combined by allreduce; the backward needs no collective.  Nothing here
+synchronises the host with the device.
 
 Replaces the per-layer Python loop of ``mafed/methods/distillation.py:105-166`` and the autograd
 chains behind ``:226-249``.
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -32,6 +42,8 @@ class DistillPlan:
     cls: bool = False
     n_vis: int = 256
     grad_multiplier: float = 1.0            # e.g. world_size to undo DDP's gradient averaging
+    single_pass: bool = True                # one-pass step when gradients are needed
+    assumed_grad_out: float = 1.0           # upstream gradient the one-pass step bakes in
     _weights: Optional[cabi.Weights] = field(default=None, repr=False)
 
     def weights(self) -> cabi.Weights:
@@ -55,17 +67,12 @@ def _require_cuda(t: torch.Tensor, what: str):
             "(there is no CPU fallback)")
 
 
-def _prepare(tensors: Sequence[torch.Tensor], dtype=None):
-    out = []
-    for t in tensors:
-        if dtype is not None and t.dtype != dtype:
-            t = t.to(dtype)
-        out.append(t if t.is_contiguous() else t.contiguous())
-    return out
+def _prepare(tensors: Sequence[torch.Tensor]):
+    return [t if t.is_contiguous() else t.contiguous() for t in tensors]
 
 
 class _Launch:
-    """Geometry + pointer tables of one step; keeps the tensors alive until the call returns."""
+    """Geometry + pointer tables of one step; keeps the tensors alive until the kernels are queued."""
 
     def __init__(self, students, teachers, attn_mask, plan: DistillPlan):
         s0 = students[0]
@@ -98,46 +105,19 @@ class _Launch:
         self.n_layers = len(students)
         self.shape = cabi.make_shape(self.n_layers, self.B, self.T, n_vis if not plan.cls else min(n_vis, self.T),
                                      self.D, _DTYPES[self.dtype], plan.loss_kind, plan.cls)
+        self.shape_ref = ctypes.byref(self.shape)
         self.students = students
         self.teachers = teachers
         self.s_ptrs = cabi.ptr_array([t.data_ptr() for t in students])
         self.t_ptrs = cabi.ptr_array([t.data_ptr() for t in teachers])
         self.mask_ptr = self.mask.data_ptr() if self.mask is not None else None
 
-
-def distill_forward(students, teachers, attn_mask, plan: DistillPlan, group=None):
-    """Run the fused forward.  Returns ``(out, bwd_scale, launch)``.
-
-    ``out`` is a device fp32 vector ``[1 + 3L]``: total loss, L layer losses (what the reference
-    logs to W&B, ``distillation.py:165``), then L x (text loss, vision loss).
-    """
-    lib = cabi.load()
-    ln = _Launch(students, teachers, attn_mask, plan)
-    L = ln.n_layers
-    dev = ln.device
-    with torch.cuda.device(dev):
-        stream = _stream_ptr(dev)
+    def alloc_scalars(self, lib):
+        L, dev = self.n_layers, self.device
         ws = torch.empty(lib.mafed_distill_ws_bytes(L), dtype=torch.uint8, device=dev)
         out = torch.empty(1 + 3 * L, dtype=torch.float32, device=dev)
         bwd_scale = torch.empty(2 * L, dtype=torch.float32, device=dev)
-        import ctypes
-        cabi.check(lib.mafed_distill_fwd(ctypes.byref(ln.shape), ln.s_ptrs, ln.t_ptrs, ln.mask_ptr, ws.data_ptr(),
-                                         stream), "mafed_distill_fwd")
-        w = plan.weights()
-        distributed, pg = resolve_group(group)
-        if distributed:
-            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
-            cabi.check(lib.mafed_distill_reduce(ctypes.byref(ln.shape), ln.mask_ptr, ws.data_ptr(), sums.data_ptr(),
-                                                stream), "mafed_distill_reduce")
-            allreduce_sums(sums, pg)
-            cabi.check(lib.mafed_distill_finalize(ctypes.byref(ln.shape), ctypes.byref(w), sums.data_ptr(),
-                                                  out.data_ptr(), bwd_scale.data_ptr(), stream),
-                       "mafed_distill_finalize")
-        else:
-            cabi.check(lib.mafed_distill_epilogue(ctypes.byref(ln.shape), ctypes.byref(w), ln.mask_ptr, ws.data_ptr(),
-                                                  None, out.data_ptr(), bwd_scale.data_ptr(), stream),
-                       "mafed_distill_epilogue")
-    return out, bwd_scale, ln
+        return ws, out, bwd_scale
 
 
 def resolve_group(group):
@@ -153,21 +133,101 @@ def resolve_group(group):
 
 
 def allreduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
-    """The path's only collective: SUM-allreduce of the ``[2L+2]`` fp64 partial sums + token counts."""
+    """The path's collective: SUM-allreduce of fp64 partial sums and/or token counts (<= 2L+2 values)."""
     torch.distributed.all_reduce(sums, op=torch.distributed.ReduceOp.SUM, group=group)
     return sums
 
 
+def distill_forward(students, teachers, attn_mask, plan: DistillPlan, group=None):
+    """Two-pass step, first half: fused forward + epilogue.  Returns ``(out, bwd_scale, launch)``.
+
+    ``out`` is a device fp32 vector ``[1 + 3L]``: total loss, L layer losses (what the reference
+    logs to W&B, ``distillation.py:165``), then L x (text loss, vision loss).
+    """
+    lib = cabi.load()
+    ln = _Launch(students, teachers, attn_mask, plan)
+    L, dev = ln.n_layers, ln.device
+    with torch.cuda.device(dev):
+        stream = _stream_ptr(dev)
+        ws, out, bwd_scale = ln.alloc_scalars(lib)
+        cabi.check(lib.mafed_distill_fwd(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, ln.mask_ptr, ws.data_ptr(), stream),
+                   "mafed_distill_fwd")
+        w = ctypes.byref(plan.weights())
+        distributed, pg = resolve_group(group)
+        if distributed:
+            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
+            cabi.check(lib.mafed_distill_reduce(ln.shape_ref, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream),
+                       "mafed_distill_reduce")
+            allreduce_sums(sums, pg)
+            cabi.check(lib.mafed_distill_finalize(ln.shape_ref, w, sums.data_ptr(), out.data_ptr(),
+                                                  bwd_scale.data_ptr(), stream), "mafed_distill_finalize")
+        else:
+            cabi.check(lib.mafed_distill_epilogue(ln.shape_ref, w, ln.mask_ptr, ws.data_ptr(), None, out.data_ptr(),
+                                                  bwd_scale.data_ptr(), stream), "mafed_distill_epilogue")
+    return out, bwd_scale, ln
+
+
 def distill_backward(ln: _Launch, grads: Sequence[Optional[torch.Tensor]], bwd_scale: torch.Tensor,
-                     grad_out: Optional[torch.Tensor]):
-    """Run the fused backward into pre-allocated ``grads`` (``None`` entries are skipped)."""
-    import ctypes
+                     grad_out: Optional[torch.Tensor], skip_if_equals: Optional[float] = None):
+    """Fused backward into pre-allocated ``grads`` (``None`` entries are skipped).  With
+    ``skip_if_equals`` the launch is the one-pass step's fix-up: a no-op on the device when the
+    upstream gradient equals that value."""
     lib = cabi.load()
     g_ptrs = cabi.ptr_array([g.data_ptr() if g is not None else None for g in grads])
+    skip = ctypes.byref(ctypes.c_float(skip_if_equals)) if skip_if_equals is not None else None
     with torch.cuda.device(ln.device):
-        cabi.check(lib.mafed_distill_bwd(ctypes.byref(ln.shape), ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr,
+        cabi.check(lib.mafed_distill_bwd(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr,
                                          bwd_scale.data_ptr(), grad_out.data_ptr() if grad_out is not None else None,
-                                         _stream_ptr(ln.device)), "mafed_distill_bwd")
+                                         skip, _stream_ptr(ln.device)), "mafed_distill_bwd")
+
+
+def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group=None):
+    """One-pass step: prologue (counts -> gradient scale), the fused kernel (loss sums + gradients from
+    one read of student and teacher), epilogue (losses).  Returns ``(out, bwd_scale, launch)``."""
+    lib = cabi.load()
+    ln = _Launch(students, teachers, attn_mask, plan)
+    L, dev = ln.n_layers, ln.device
+    fixed = float(plan.assumed_grad_out) * float(plan.grad_multiplier)
+    g_ptrs = cabi.ptr_array([g.data_ptr() if g is not None else None for g in grads])
+    with torch.cuda.device(dev):
+        stream = _stream_ptr(dev)
+        ws, out, bwd_scale = ln.alloc_scalars(lib)
+        w = ctypes.byref(plan.weights())
+        distributed, pg = resolve_group(group)
+        if distributed:
+            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
+            cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_COUNTS, ln.mask_ptr, None,
+                                                      sums.data_ptr(), None, None, stream), "counts")
+            allreduce_sums(sums[2 * L:], pg)
+            cabi.check(lib.mafed_distill_prologue(ln.shape_ref, w, None, sums.data_ptr(), None, bwd_scale.data_ptr(),
+                                                  stream), "mafed_distill_prologue")
+        else:
+            cabi.check(lib.mafed_distill_prologue(ln.shape_ref, w, ln.mask_ptr, None, None, bwd_scale.data_ptr(),
+                                                  stream), "mafed_distill_prologue")
+        cabi.check(lib.mafed_distill_fused(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr,
+                                           bwd_scale.data_ptr(), fixed, ws.data_ptr(), stream), "mafed_distill_fused")
+        if distributed:
+            cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_REDUCE, None, ws.data_ptr(),
+                                                      sums.data_ptr(), None, None, stream), "reduce")
+            allreduce_sums(sums[: 2 * L], pg)
+            cabi.check(lib.mafed_distill_finalize(ln.shape_ref, w, sums.data_ptr(), out.data_ptr(), None, stream),
+                       "mafed_distill_finalize")
+        else:
+            cabi.check(lib.mafed_distill_epilogue(ln.shape_ref, w, ln.mask_ptr, ws.data_ptr(), None, out.data_ptr(),
+                                                  None, stream), "mafed_distill_epilogue")
+    return out, bwd_scale, ln
+
+
+def _alloc_grads(students, needs: Sequence[bool], cls: bool):
+    grads = []
+    for s, need in zip(students, needs):
+        if not need:
+            grads.append(None)
+        elif cls:
+            grads.append(torch.zeros_like(s))  # only row 0 of each sample is written by the kernel
+        else:
+            grads.append(torch.empty_like(s))
+    return grads
 
 
 class _DistillFunction(torch.autograd.Function):
@@ -175,38 +235,39 @@ class _DistillFunction(torch.autograd.Function):
     def forward(ctx, plan: DistillPlan, attn_mask, group, n, *tensors):
         students = _prepare(tensors[:n])
         teachers = _prepare(tensors[n:])
-        out, bwd_scale, ln = distill_forward(students, teachers, attn_mask, plan, group)
-        ctx.launch = ln
-        ctx.plan = plan
-        ctx.bwd_scale = bwd_scale
-        ctx.n = n
-        total = out[0]
-        aux = out[1:]
+        needs = list(ctx.needs_input_grad[4:4 + n])
+        ctx.plan, ctx.n, ctx.needs, ctx.grads = plan, n, needs, None
+        if plan.single_pass and any(needs):
+            grads = _alloc_grads(students, needs, plan.cls)
+            out, bwd_scale, ln = distill_fused(students, teachers, grads, attn_mask, plan, group)
+            ctx.grads = grads
+        else:
+            out, bwd_scale, ln = distill_forward(students, teachers, attn_mask, plan, group)
+        ctx.launch, ctx.bwd_scale = ln, bwd_scale
+        total, aux = out[0], out[1:]
         ctx.mark_non_differentiable(aux)
         return total, aux
 
     @staticmethod
     def backward(ctx, grad_total, _grad_aux):
         ln, plan, n = ctx.launch, ctx.plan, ctx.n
-        if grad_total is None:
-            return (None,) * (4 + 2 * n)
+        none = (None,) * (4 + 2 * n)
+        if grad_total is None or ln is None or not any(ctx.needs):
+            return none
         g = grad_total
-        if g.dtype != torch.float32 or not g.is_cuda:
+        if g.dtype != torch.float32 or g.device != ln.device:
             g = g.to(device=ln.device, dtype=torch.float32)
         if plan.grad_multiplier != 1.0:
             g = g * plan.grad_multiplier
         g = g.contiguous()
-        grads = []
-        for i, s in enumerate(ln.students):
-            if not ctx.needs_input_grad[4 + i]:
-                grads.append(None)
-            elif plan.cls:
-                grads.append(torch.zeros_like(s))  # only row 0 of each sample is written by the kernel
-            else:
-                grads.append(torch.empty_like(s))
-        if any(x is not None for x in grads):
+        if ctx.grads is not None:
+            # one-pass step: gradients already exist; fix them up only if the upstream gradient differs
+            grads, ctx.grads = ctx.grads, None
+            fixed = float(plan.assumed_grad_out) * float(plan.grad_multiplier)
+            distill_backward(ln, grads, ctx.bwd_scale, g, skip_if_equals=fixed)
+        else:
+            grads = _alloc_grads(ln.students, ctx.needs, plan.cls)
             distill_backward(ln, grads, ctx.bwd_scale, g)
-        ctx.launch = None
         return (None, None, None, None, *grads, *([None] * n))
 
 
@@ -215,7 +276,7 @@ def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tens
     """Differentiable fused distillation loss over ``len(students)`` selected layers.
 
     Returns ``(total, aux)``: ``total`` is the 0-dim fp32 loss (gradients flow to ``students``),
-    ``aux`` the non-differentiable ``[3L]`` vector of layer / modality losses.
+    ``aux`` the non-differentiable ``[3L]`` vector of layer losses then (text, vision) losses.
     """
     students = list(students)
     teachers = [t.detach() for t in teachers]

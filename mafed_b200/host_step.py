@@ -5,7 +5,7 @@ device: every step copies student / teacher / mask host -> device, runs the fuse
 epilogue and backward, and copies the gradients and the loss device -> host.  Layers are
 pipelined over three streams (copy-in, compute, copy-out) so that PCIe transfers in both directions
 overlap each other and the kernels; per layer the work is three C-ABI launches
-(``mafed_distill_fwd`` / ``_epilogue`` / ``_bwd`` with ``n_layers = 1``).
+(``mafed_distill_prologue`` / ``_fused`` / ``_epilogue`` with ``n_layers = 1``).
 
 The backward of a layer needs only the token counts and the host weight tables, not the other
 layers' sums, which is what makes the per-layer pipeline legal.
@@ -16,7 +16,7 @@ from typing import List
 
 import torch
 
-from mafed_b200.distill_op import distill_backward, distill_forward
+from mafed_b200.distill_op import distill_fused
 
 
 class HostStep:
@@ -46,13 +46,14 @@ class HostStep:
         nbytes = lambda ts: sum(t.numel() * t.element_size() for t in ts)
         self.h2d_bytes = nbytes(self.h_s) + nbytes(self.h_t) + nbytes([self.h_mask])
         self.d2h_bytes = nbytes(self.h_g) + 4 * (1 + len(students))
-        self.note = "pinned host student/teacher/mask -> device, fwd+epilogue+bwd per layer, gradients+loss -> pinned host; " \
+        self.note = "pinned host student/teacher/mask -> device, one-pass fused kernel per layer, gradients+loss -> pinned host; " \
                     "3-stream layer pipeline"
         coeffs, kind, lang = method._tables(self.layers)
         self.plans = []
         for i, l in enumerate(self.layers):
-            self.plans.append(method._plan([l], [coeffs[i]], method.distillation_coeff, kind,
-                                           None if lang is None else [lang[i]]))
+            plan = method._plan([l], [coeffs[i]], method.distillation_coeff, kind, None if lang is None else [lang[i]])
+            plan.assumed_grad_out = 1.0
+            self.plans.append(plan)
 
     def step(self) -> torch.Tensor:
         """One end-to-end step.  Returns the pinned host 0-dim loss (valid on return)."""
@@ -68,9 +69,9 @@ class HostStep:
         outs = []
         for i in range(len(self.layers)):
             cur.wait_event(self.ev_in[i])
-            out, scale, ln = distill_forward([self.d_s[i]], [self.d_t[i]], self.d_mask, self.plans[i],
-                                             group=self.method.process_group)
-            distill_backward(ln, [self.d_g[i]], scale, self.gout)
+            # upstream gradient is a host value here (1.0), so the one-pass kernel's result is final
+            out, _, _ = distill_fused([self.d_s[i]], [self.d_t[i]], [self.d_g[i]], self.d_mask, self.plans[i],
+                                      group=self.method.process_group)
             self.ev_done[i].record(cur)
             outs.append(out)
             with torch.cuda.stream(self.s_out):

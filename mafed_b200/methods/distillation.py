@@ -85,6 +85,10 @@ class FeatureDistillation(CLStrategy):
         # ---- B200 path state
         self.process_group = kwargs.get("process_group")   # None: default group when initialised
         self.populate_batch_masks = True                    # keep the reference's side effect on `batch`
+        # one-pass step (loss sums and gradients from a single read of student and teacher); the upstream
+        # gradient it bakes in is Lightning's 1/accumulate_grad_batches, checked on the device in backward
+        self.single_pass = bool(kwargs.get("single_pass", True))
+        self.assumed_grad_out = 1.0 / float(self.update_freq)
         self.last_layer_losses: Optional[torch.Tensor] = None   # device [3L]: layer, then (text, vision)
         self.last_layers: List[int] = []
         self._pending_log = None
@@ -169,7 +173,8 @@ class FeatureDistillation(CLStrategy):
                             "(MSELoss.forward() takes 3 positional arguments but 4 were given)")
         return DistillPlan(layers=list(layers), layer_coeffs=list(coeffs), distill_coeff=float(distill_coeff),
                            modality_kind=modality_kind, lang_weights=lang_weights, loss_kind=self._loss_kind,
-                           cls=bool(self._cls_distillation), n_vis=self.num_vision_tokens)
+                           cls=bool(self._cls_distillation), n_vis=self.num_vision_tokens,
+                           single_pass=self.single_pass, assumed_grad_out=self.assumed_grad_out)
 
     def _launch(self, plan: DistillPlan, batch, students, teachers):
         attn = None

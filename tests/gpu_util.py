@@ -35,11 +35,13 @@ def make_method(meta, **extra):
     return fd
 
 
-def run_product(meta, students, teachers, mask, grad_out=1.0, variant=cabi.VARIANT_DEFAULT, dev="cuda"):
+def run_product(meta, students, teachers, mask, grad_out=1.0, variant=cabi.VARIANT_DEFAULT, dev="cuda",
+                single_pass=True, accumulate=1):
     """distill() + backward() on the GPU through the mirrored strategy API."""
     cabi.load().mafed_distill_set_variant(variant)
     try:
-        fd = make_method(meta)
+        fd = make_method(meta, single_pass=single_pass)
+        fd.assumed_grad_out = 1.0 / accumulate
         st = [s.to(dev).detach().clone().requires_grad_(True) for s in students]
         te = [t.to(dev) for t in teachers]
         fd.past_model = lambda **kw: Out(tuple(te))
