@@ -19,6 +19,7 @@ ABI_VERSION = 2
 PASS_FWD, PASS_BWD, PASS_FUSED = 0, 1, 2
 TUNE_TMA_STAGES, TUNE_TMA_ROWS, TUNE_VARIANT = 0, 3, 6
 TUNE_TMA_WARPS, TUNE_LDG_BLOCKS_PER_SM, TUNE_BWD_FORWARD_ORDER, TUNE_GRID_MUL = 9, 10, 11, 12
+TUNE_LOAD_POLICY, TUNE_STORE_POLICY = 13, 14   # 0 none, 1 evict_first, 2 evict_last, 3 evict_normal
 N_TUNE_KEYS = 16
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmafed_distill.so")

@@ -20,7 +20,7 @@ std::atomic<int> g_tune[16] = {};  // experiment knobs, see mafed_distill_set_tu
 
 // per-pass keys: base + pass (fwd, bwd, fused)
 enum TuneKey { kTuneTmaStages = 0, kTuneTmaRows = 3, kTuneVariant = 6, kTuneTmaWarps = 9, kTuneLdgBlocksPerSm = 10,
-               kTuneBwdForward = 11, kTuneGridMul = 12 };
+               kTuneBwdForward = 11, kTuneGridMul = 12, kTuneLoadPolicy = 13, kTuneStorePolicy = 14 };
 
 struct DeviceInfo {
   int sm_count = 0;
@@ -142,7 +142,9 @@ bool tma_geometry(const PathParams& p, int pass, TmaGeom& geo) {
   const long long budget = (long long)dv.smem_optin - 16 * 1024;  // static smem + slack
   int rows = g_tune[kTuneTmaRows + pass].load();
   if (rows <= 0) {
-    const long long stage_target = 65536;
+    // Measured on B200 (profiles/r01_call3_sweep_step.json): a ring of 2 stages x 64-72 KB per SM is the
+    // sweet spot for every pass; deeper rings (>= 192 KB in flight per SM) cost 4-8 % of HBM throughput.
+    const long long stage_target = 72 * 1024;
     rows = (int)(stage_target / (2 * row_bytes));
     if (rows >= 8) rows &= ~7;
   }
@@ -153,7 +155,7 @@ bool tma_geometry(const PathParams& p, int pass, TmaGeom& geo) {
   geo.rows = rows;
   geo.stage_bytes = (int)(2 * rows * row_bytes);
   int stages = g_tune[kTuneTmaStages + pass].load();
-  if (stages <= 0) stages = 4;
+  if (stages <= 0) stages = (2 * geo.stage_bytes >= 96 * 1024) ? 2 : 3;
   if (stages > kTmaMaxStages) stages = kTmaMaxStages;
   while (stages > 1 && (long long)stages * geo.stage_bytes > budget) --stages;
   geo.stages = stages;
@@ -215,6 +217,8 @@ int dispatch(const mafed_shape_t& sh, PathParams& p, int pass, cudaStream_t st) 
   for (int l = 0; l < sh.n_layers && vector_ok; ++l)
     vector_ok = aligned_to(p.s[l], 16) && aligned_to(p.t[l], 16) && (pass == kPassFwd || aligned_to(p.g[l], 16));
   p.n_chunks = vector_ok ? (int)((size_t)sh.D * es / 16) : 0;
+  p.load_policy = g_tune[kTuneLoadPolicy].load();
+  p.store_policy = g_tune[kTuneStorePolicy].load();
   switch (sh.dtype) {
     case MAFED_F32: return dispatch_loss<float>(p, sh.loss_kind, vector_ok, pass, st);
     case MAFED_BF16: return dispatch_loss<__nv_bfloat16>(p, sh.loss_kind, vector_ok, pass, st);

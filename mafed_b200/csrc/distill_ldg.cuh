@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(kLdgThreads, kLdgMinBlocks) k_fwd_ldg(const __
   const long long total = groups_per_layer * p.n_layers;
   const int n_pass = (CPL == 8) ? (p.n_chunks + 32 * CPL - 1) / (32 * CPL) : 1;
   const long long row_bytes = p.row_stride * (long long)sizeof(T);
+  const uint64_t lpol = make_policy(p.load_policy);
 
   float acc_text = 0.f, acc_vis = 0.f;
   int cur = -1;
@@ -61,8 +62,8 @@ __global__ void __launch_bounds__(kLdgThreads, kLdgMinBlocks) k_fwd_ldg(const __
         for (int i = 0; i < CPL; ++i) {
           const int c = pass * 32 * CPL + lane + 32 * i;
           if (w[r] != 0.f && c < p.n_chunks) {
-            sv[r][i] = ldg_stream(sb + off + (long long)c * 16);
-            tv[r][i] = ldg_stream(tb + off + (long long)c * 16);
+            sv[r][i] = ldg_stream(sb + off + (long long)c * 16, p.load_policy, lpol);
+            tv[r][i] = ldg_stream(tb + off + (long long)c * 16, p.load_policy, lpol);
           } else {
             sv[r][i] = make_uint4(0, 0, 0, 0);
             tv[r][i] = make_uint4(0, 0, 0, 0);
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(kLdgThreads, kLdgMinBlocksBwd) k_bwd_ldg(const
   constexpr bool FUSED = MODE == kFused;
   __shared__ CtaSums<FUSED ? kLdgWarps : 1> sums;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t spol = make_policy(p.store_policy), lpol = make_policy(p.load_policy);
   float gout;
   if (!upstream_grad<MODE>(p, gout)) return;
   if (FUSED) {
@@ -203,8 +205,8 @@ __global__ void __launch_bounds__(kLdgThreads, kLdgMinBlocksBwd) k_bwd_ldg(const
         for (int i = 0; i < CPL; ++i) {
           const int c = pass * 32 * CPL + lane + 32 * i;
           if (wraw[r] != 0.f && c < p.n_chunks) {
-            sv[r][i] = ldg_stream(sb + off + (long long)c * 16);
-            tv[r][i] = ldg_stream(tb + off + (long long)c * 16);
+            sv[r][i] = ldg_stream(sb + off + (long long)c * 16, p.load_policy, lpol);
+            tv[r][i] = ldg_stream(tb + off + (long long)c * 16, p.load_policy, lpol);
           } else {
             sv[r][i] = make_uint4(0, 0, 0, 0);
             tv[r][i] = make_uint4(0, 0, 0, 0);
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kLdgThreads, kLdgMinBlocksBwd) k_bwd_ldg(const
           } else {
             grad_elems<LOSS, NE>(a, b, w[r], ch[r], cp[r], o);
           }
-          if (gb != nullptr) stg_128(gb + off + (long long)c * 16, Pack<T>::pack(o));
+          if (gb != nullptr) stg_128(gb + off + (long long)c * 16, Pack<T>::pack(o), p.store_policy, spol);
         }
       }
     }

@@ -50,9 +50,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!ok);
 }
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0).
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, int kind,
+                                         uint64_t pol) {
+  if (kind == kPolicyNone) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  } else {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+  }
 }
 __device__ __forceinline__ uint4 lds_128(uint32_t addr) {
   uint4 r;
@@ -74,6 +80,7 @@ __device__ __forceinline__ void tma_producer(const PathParams& p, const TmaGeom&
   const uint32_t row_bytes = (uint32_t)p.n_chunks * 16u;
   const long long row_pitch = p.row_stride * (long long)sizeof(T);
   const bool contiguous = row_pitch == (long long)row_bytes;
+  const uint64_t lpol = make_policy(p.load_policy);
   int stage = 0;
   uint32_t phase = 0;
   for (long long t0 = blockIdx.x; t0 < total; t0 += gridDim.x) {
@@ -103,12 +110,12 @@ __device__ __forceinline__ void tma_producer(const PathParams& p, const TmaGeom&
     const unsigned all = (n_rows >= 32) ? 0xffffffffu : ((1u << n_rows) - 1u);
     if (contiguous && valid == all) {
       // whole tile live: one bulk copy per tensor
-      if (lane == 0) bulk_g2s(s_dst, sb, (uint32_t)n_rows * row_bytes, bar);
-      if (lane == 1) bulk_g2s(t_dst, tb, (uint32_t)n_rows * row_bytes, bar);
+      if (lane == 0) bulk_g2s(s_dst, sb, (uint32_t)n_rows * row_bytes, bar, p.load_policy, lpol);
+      if (lane == 1) bulk_g2s(t_dst, tb, (uint32_t)n_rows * row_bytes, bar, p.load_policy, lpol);
     } else if (w != 0.f) {
       // ragged tile: only live rows are fetched (padded text rows cost no bandwidth)
-      bulk_g2s(s_dst + (uint32_t)lane * row_bytes, sb + (long long)lane * row_pitch, row_bytes, bar);
-      bulk_g2s(t_dst + (uint32_t)lane * row_bytes, tb + (long long)lane * row_pitch, row_bytes, bar);
+      bulk_g2s(s_dst + (uint32_t)lane * row_bytes, sb + (long long)lane * row_pitch, row_bytes, bar, p.load_policy, lpol);
+      bulk_g2s(t_dst + (uint32_t)lane * row_bytes, tb + (long long)lane * row_pitch, row_bytes, bar, p.load_policy, lpol);
     }
     if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
   }
@@ -236,6 +243,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
   __shared__ TmaSmem sm;
   __shared__ CtaSums<FUSED ? NCW : 1> sums;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t spol = make_policy(p.store_policy);
   float gout;
   if (FUSED) {
     gout = p.fixed_gout;
@@ -281,7 +289,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
           for (int i = 0; i < NE; ++i) o[i] = w;
           const uint4 fill = Pack<T>::pack(o);
           if (gb != nullptr)
-            for (int c = lane; c < p.n_chunks; c += 32) stg_128(grow + (long long)c * 16, fill);
+            for (int c = lane; c < p.n_chunks; c += 32) stg_128(grow + (long long)c * 16, fill, p.store_policy, spol);
           continue;
         }
         const uint32_t sa = s_base + (uint32_t)r * row_bytes, ta = t_base + (uint32_t)r * row_bytes;
@@ -318,7 +326,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
               accumulate<LOSS, NE>(a, b, rowval, y, z);
             }
             grad_elems_tma<LOSS, NE>(a, b, w, ch, cp, o);
-            if (gb != nullptr) stg_128(grow + (long long)(c + 32 * u) * 16, Pack<T>::pack(o));
+            if (gb != nullptr) stg_128(grow + (long long)(c + 32 * u) * 16, Pack<T>::pack(o), p.store_policy, spol);
           }
         }
         for (; c < p.n_chunks; c += 32) {
@@ -330,7 +338,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
             accumulate<LOSS, NE>(a, b, rowval, y, z);
           }
           grad_elems_tma<LOSS, NE>(a, b, w, ch, cp, o);
-          if (gb != nullptr) stg_128(grow + (long long)c * 16, Pack<T>::pack(o));
+          if (gb != nullptr) stg_128(grow + (long long)c * 16, Pack<T>::pack(o), p.store_policy, spol);
         }
         if (FUSED) {
           if (mt.mod[r] == 0) acc_text = fmaf(mt.w[r], rowval, acc_text);
