@@ -145,6 +145,12 @@ int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_p
                         const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
                         const float* bwd_scale, float assumed_grad_out, void* ws, void* stream);
 
+/* The two [B, T] int64 masks the reference stores into the batch dict (distillation.py:134-144):
+ * lang_mask[:, n_vis:] = attn_mask, image_mask[:, :n_vis] = 1, zeros elsewhere -- one launch, on the
+ * device (the reference builds them on the CPU and copies them over, per layer). */
+int mafed_distill_modality_masks(const mafed_shape_t* shape, const int64_t* attn_mask, int64_t* lang_mask,
+                                 int64_t* image_mask, void* stream);
+
 /* Experiment knobs (benchmarks only; process-global): kernel family for the next calls
  * (0 = default, 1 = ldg: register-staged 128-bit loads, 2 = tma: cp.async.bulk + mbarrier ring),
  * and integer tuning keys (see mafed_b200/cabi.py). */

@@ -20,7 +20,26 @@ std::atomic<int> g_tune[16] = {};  // experiment knobs, see mafed_distill_set_tu
 
 // per-pass keys: base + pass (fwd, bwd, fused)
 enum TuneKey { kTuneTmaStages = 0, kTuneTmaRows = 3, kTuneVariant = 6, kTuneTmaWarps = 9, kTuneLdgBlocksPerSm = 10,
-               kTuneBwdForward = 11, kTuneGridMul = 12, kTuneLoadPolicy = 13, kTuneStorePolicy = 14 };
+               kTuneBwdForward = 11, kTuneGridMul = 12, kTuneLoadPolicy = 13, kTuneStorePolicy = 14, kTuneNoPdl = 15 };
+
+// Launch with programmatic dependent launch enabled: the kernel may start its prologue while its
+// predecessor in the stream is finishing; all kernels here call griddepcontrol.wait before touching
+// global memory, so stream-order semantics are unchanged.
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_tune[kTuneNoPdl].load() ? 0 : 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 struct DeviceInfo {
   int sm_count = 0;
@@ -106,9 +125,9 @@ int launch_ldg(const PathParams& p, int pass, cudaStream_t st) {
   const long long rows_per_iter = (long long)kLdgWarps * RPI;
   const long long total = ((p.n_rows + rows_per_iter - 1) / rows_per_iter) * p.n_layers;
   const unsigned grid = (unsigned)clamp_grid((long long)dv.sm_count * per_sm, total);
-  if (pass == kPassFwd) k_fwd_ldg<T, CPL, RPI, LOSS><<<grid, kLdgThreads, 0, st>>>(p);
-  else if (pass == kPassBwd) k_bwd_ldg<T, CPL, RPI, LOSS, kBackward><<<grid, kLdgThreads, 0, st>>>(p);
-  else k_bwd_ldg<T, CPL, RPI, LOSS, kFused><<<grid, kLdgThreads, 0, st>>>(p);
+  if (pass == kPassFwd) launch_pdl(k_fwd_ldg<T, CPL, RPI, LOSS>, grid, kLdgThreads, 0, st, p);
+  else if (pass == kPassBwd) launch_pdl(k_bwd_ldg<T, CPL, RPI, LOSS, kBackward>, grid, kLdgThreads, 0, st, p);
+  else launch_pdl(k_bwd_ldg<T, CPL, RPI, LOSS, kFused>, grid, kLdgThreads, 0, st, p);
   return (int)cudaPeekAtLastError();
 }
 
@@ -129,9 +148,9 @@ int launch_generic(const PathParams& p, int pass, cudaStream_t st) {
   const DeviceInfo& dv = device_info();
   const long long total = ((p.n_rows + kLdgWarps - 1) / kLdgWarps) * p.n_layers;
   const unsigned grid = (unsigned)clamp_grid((long long)dv.sm_count * 4, total);
-  if (pass == kPassFwd || pass == kPassFused) k_fwd_generic<T, LOSS><<<grid, kLdgThreads, 0, st>>>(p);
+  if (pass == kPassFwd || pass == kPassFused) launch_pdl(k_fwd_generic<T, LOSS>, grid, kLdgThreads, 0, st, p);
   if (pass == kPassBwd || pass == kPassFused)
-    k_bwd_generic<T, LOSS><<<grid, kLdgThreads, 0, st>>>(p, pass == kPassFused ? 1 : 0);
+    launch_pdl(k_bwd_generic<T, LOSS>, grid, kLdgThreads, 0, st, p, pass == kPassFused ? 1 : 0);
   return (int)cudaPeekAtLastError();
 }
 
@@ -182,9 +201,9 @@ int launch_tma(const PathParams& p, const TmaGeom& geo, int pass, cudaStream_t s
   if (mul <= 0) mul = 1;
   const unsigned grid = (unsigned)clamp_grid((long long)dv.sm_count * mul, total);
   constexpr int threads = (NCW + 1) * 32;
-  if (pass == kPassFwd) k_fwd_tma<T, LOSS, NCW><<<grid, threads, dyn, st>>>(p, geo);
-  else if (pass == kPassBwd) k_bwd_tma<T, LOSS, NCW, kBackward><<<grid, threads, dyn, st>>>(p, geo);
-  else k_bwd_tma<T, LOSS, NCW, kFused><<<grid, threads, dyn, st>>>(p, geo);
+  if (pass == kPassFwd) launch_pdl(k_fwd_tma<T, LOSS, NCW>, grid, threads, dyn, st, p, geo);
+  else if (pass == kPassBwd) launch_pdl(k_bwd_tma<T, LOSS, NCW, kBackward>, grid, threads, dyn, st, p, geo);
+  else launch_pdl(k_bwd_tma<T, LOSS, NCW, kFused>, grid, threads, dyn, st, p, geo);
   return (int)cudaPeekAtLastError();
 }
 
@@ -197,8 +216,10 @@ int dispatch_typed(PathParams& p, bool vector_ok, int pass, cudaStream_t st) {
   if (variant == 2) {
     TmaGeom geo;
     if (tma_geometry(p, pass, geo)) {
-      if (g_tune[kTuneTmaWarps].load() == 16) return launch_tma<T, LOSS, 16>(p, geo, pass, st);
-      return launch_tma<T, LOSS, 8>(p, geo, pass, st);
+      // 16 consumer warps: two stages are drained concurrently when a stage holds <= 8 rows (+2.6 % on the
+      // 1B shape, neutral elsewhere; profiles/r01_call4_sweep_extra.json)
+      if (g_tune[kTuneTmaWarps].load() == 8) return launch_tma<T, LOSS, 8>(p, geo, pass, st);
+      return launch_tma<T, LOSS, 16>(p, geo, pass, st);
     }
   }
   return dispatch_ldg<T, LOSS>(p, pass, st);
@@ -266,7 +287,7 @@ int launch_scalar_stage(const mafed_shape_t& sh, const mafed_weights_t* w, int f
   e.loss_kind = sh.loss_kind;
   e.flags = flags;
   if (w != nullptr) e.w = *w;
-  k_epilogue<<<1, kEpiThreads, 0, st>>>(e);
+  launch_pdl(k_epilogue, 1, kEpiThreads, 0, st, e);
   return (int)cudaPeekAtLastError();
 }
 
@@ -381,6 +402,18 @@ int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_p
   p.fixed_gout = assumed_grad_out;
   p.ws = reinterpret_cast<float*>(ws);
   return dispatch(*shape, p, kPassFused, (cudaStream_t)stream);
+}
+
+int mafed_distill_modality_masks(const mafed_shape_t* shape, const int64_t* attn_mask, int64_t* lang_mask,
+                                 int64_t* image_mask, void* stream) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!lang_mask || !image_mask || (needs_mask(*shape) && !attn_mask)) return MAFED_E_ARG;
+  const long long n = (long long)shape->B * shape->T;
+  const unsigned grid = (unsigned)clamp_grid((n + 255) / 256, 1 << 20);
+  launch_pdl(k_modality_masks, grid > 1184 ? 1184u : grid, 256, 0, (cudaStream_t)stream, attn_mask, lang_mask,
+             image_mask, n, (int)shape->T, (int)shape->n_vis);
+  return (int)cudaPeekAtLastError();
 }
 
 int mafed_distill_set_variant(int variant) {

@@ -143,6 +143,14 @@ __device__ __forceinline__ void stg_128(void* p, const uint4& v, int kind, uint6
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the path is launched with programmaticStreamSerialization: it may become resident
+// while its predecessor in the stream is still running (hiding launch latency and prologue work) and
+// blocks in pdl_wait() -- before its first global-memory access -- until the predecessor has completed
+// and flushed.  pdl_launch_dependents() lets the successor do the same with respect to this kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- reductions
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -29,12 +29,29 @@ struct EpiParams {
   mafed_weights_t w;
 };
 
+// distillation.py:134-144: language mask = [0 x n_vis | attention_mask], image mask = [1 x n_vis | 0 x txt].
+__global__ void __launch_bounds__(256) k_modality_masks(const int64_t* __restrict__ attn, int64_t* __restrict__ lang,
+                                                        int64_t* __restrict__ image, long long n, int T, int n_vis) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int txt = T - n_vis;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / T;
+    const int t = (int)(i - b * T);
+    const bool vis = t < n_vis;
+    lang[i] = vis ? 0 : attn[b * txt + (t - n_vis)];
+    image[i] = vis ? 1 : 0;
+  }
+}
+
 __global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant__ EpiParams p) {
   __shared__ double s_sums[2 * kMaxLayers + 2];
   __shared__ long long s_cnt[kEpiThreads / 32];
   __shared__ double s_layer[kMaxLayers];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.n_layers;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (p.flags & kEpiReduce) {
     const int n_part = reinterpret_cast<const int*>(p.ws)[0];

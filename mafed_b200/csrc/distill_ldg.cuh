@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(kLdgThreads, kLdgMinBlocks) k_fwd_ldg(const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   cta_sums_zero(sums, p.n_layers);
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
 
   constexpr int kRowsPerIter = kLdgWarps * RPI;
   const long long groups_per_layer = (p.n_rows + kRowsPerIter - 1) / kRowsPerIter;
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(kLdgThreads, kLdgMinBlocksBwd) k_bwd_ldg(const
   __shared__ CtaSums<FUSED ? kLdgWarps : 1> sums;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t spol = make_policy(p.store_policy), lpol = make_policy(p.load_policy);
+  pdl_launch_dependents();
+  pdl_wait();
   float gout;
   if (!upstream_grad<MODE>(p, gout)) return;
   if (FUSED) {
@@ -280,6 +284,8 @@ __global__ void __launch_bounds__(kLdgThreads) k_fwd_generic(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   cta_sums_zero(sums, p.n_layers);
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
   const long long groups_per_layer = (p.n_rows + kLdgWarps - 1) / kLdgWarps;
   const long long total = groups_per_layer * p.n_layers;
   float acc_text = 0.f, acc_vis = 0.f;
@@ -317,6 +323,8 @@ __global__ void __launch_bounds__(kLdgThreads) k_bwd_generic(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long groups_per_layer = (p.n_rows + kLdgWarps - 1) / kLdgWarps;
   const long long total = groups_per_layer * p.n_layers;
+  pdl_launch_dependents();
+  pdl_wait();
   float gout;
   if (use_fixed_gout) gout = p.fixed_gout;
   else if (!upstream_grad<kBackward>(p, gout)) return;

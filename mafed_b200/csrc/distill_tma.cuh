@@ -137,6 +137,9 @@ __device__ __forceinline__ void tma_prologue(TmaSmem& sm, const TmaGeom& geo) {
     mbar_fence_init();
   }
   __syncthreads();
+  // everything above overlapped the predecessor kernel's tail; from here on we touch global memory
+  pdl_launch_dependents();
+  pdl_wait();
 }
 
 // ---------------------------------------------------------------- forward
@@ -244,6 +247,8 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
   __shared__ CtaSums<FUSED ? NCW : 1> sums;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t spol = make_policy(p.store_policy);
+  if (FUSED) cta_sums_zero(sums, p.n_layers);
+  tma_prologue<NCW>(sm, geo);
   float gout;
   if (FUSED) {
     gout = p.fixed_gout;
@@ -251,8 +256,6 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
     gout = p.grad_out ? __ldg(p.grad_out) : 1.f;
     if (p.skip_if_gout_equals && gout == p.fixed_gout) return;  // fix-up launch with nothing to fix
   }
-  if (FUSED) cta_sums_zero(sums, p.n_layers);
-  tma_prologue<NCW>(sm, geo);
   if (warp == NCW) {
     tma_producer<T>(p, geo, dyn_smem, sm.full, sm.empty, sm.meta, lane, !FUSED);
     return;

@@ -120,6 +120,25 @@ class _Launch:
         return ws, out, bwd_scale
 
 
+def modality_masks(attn_mask: torch.Tensor, n_vis: int):
+    """``[B, n_vis + txt]`` int64 language / image masks (``distillation.py:134-144``) in one launch."""
+    lib = cabi.load()
+    _require_cuda(attn_mask, "attention_mask")
+    am = attn_mask if attn_mask.dtype == torch.int64 else attn_mask.to(torch.int64)
+    am = am.contiguous()
+    B, txt = am.shape
+    both = torch.empty((2, B, n_vis + txt), dtype=torch.int64, device=am.device)
+    shape = cabi.make_shape(1, B, n_vis + txt, n_vis, 1, cabi.F32, cabi.LOSS_MSE)
+    with torch.cuda.device(am.device):
+        cabi.check(lib.mafed_distill_modality_masks(ctypes.byref(shape), am.data_ptr(), both[0].data_ptr(),
+                                                    both[1].data_ptr(), _stream_ptr(am.device)),
+                   "mafed_distill_modality_masks")
+    lang, image = both[0], both[1]
+    if attn_mask.dtype != torch.int64:
+        lang, image = lang.to(attn_mask.dtype), image.to(attn_mask.dtype)
+    return lang, image
+
+
 def resolve_group(group):
     """``None``: the default process group if one is initialised with more than one rank;
     ``False``: never communicate; otherwise an explicit ``ProcessGroup``."""

@@ -20,9 +20,9 @@ import numpy as np
 import torch
 
 from mafed_b200 import cabi
-from mafed_b200.distill_op import DistillPlan, distill_loss
+from mafed_b200.distill_op import DistillPlan, distill_loss, modality_masks
 from mafed_b200.methods.base import CLStrategy
-from mafed_b200.methods.distillation_loss_weights import DistillationWeights, modality_masks
+from mafed_b200.methods.distillation_loss_weights import DistillationWeights
 
 try:  # W&B is optional here; the reference requires it
     import wandb as _wandb

@@ -262,3 +262,18 @@ def test_sharded_partial_sums_equal_full_batch():
     _, per_layer, _ = O.distill([s.float() for s in st], [t.float() for t in te], am, cfg)
     want = sum(c * float(per_layer[l]) for l, c in zip(range(3), [0.2, 0.3, 0.5]))
     assert float(out[0]) == pytest.approx(want, rel=1e-5)
+
+
+def test_modality_masks_kernel_matches_reference_construction():
+    from mafed_b200.distill_op import modality_masks
+    from mafed_b200.methods.distillation_loss_weights import modality_masks as torch_masks
+    am = (torch.rand(7, 13, device="cuda") > 0.3).long()
+    for n_vis in (0, 1, 256):
+        a, b = modality_masks(am, n_vis)
+        c, d = torch_masks(am, n_vis)
+        assert torch.equal(a, c) and torch.equal(b, d) and a.dtype == torch.int64
+    lang, img = O.build_masks(am.cpu(), 256)  # distillation.py:134-144
+    a, b = modality_masks(am, 256)
+    assert torch.equal(a.cpu(), lang) and torch.equal(b.cpu(), img)
+    a32, _ = modality_masks(am.int(), 4)
+    assert a32.dtype == torch.int32
