@@ -115,3 +115,20 @@ def test_cpu_tensors_are_refused_loudly():
     s = torch.randn(1, 3, 8, requires_grad=True)
     with pytest.raises(cabi.MafedDistillError, match="no CPU fallback"):
         distill_loss([s], [torch.randn(1, 3, 8)], torch.ones(1, 1, dtype=torch.int64), plan, group=False)
+
+
+def test_constructed_exactly_like_train_py():
+    """mafed/train.py:119-134 keyword set, including the ones the strategy swallows."""
+    fd = CLMethod["featdistill"](
+        opts=Opts(), memory_size=500, model_type="vlpythia", scaler=object(), reg_lambda=1.0, replay_coeff=1.0,
+        distillation_coeff=1.0, distillation_modality_weighing_strategy="balanced",
+        distillation_layer_weighing_strategy="discounted", distillation_layer=None, cls_distillation=False,
+        distillation_loss="mse", gamma=0.5, num_hidden_layers=15)
+    assert fd.loss_weights.get_distillation_layers() == list(range(15))
+    assert fd.memory_per_task == 250 and fd.assumed_grad_out == 0.25 and fd.single_pass
+    assert fd.replay_coeff == 1.0 and fd.distillation_coeff == 1.0 and fd.task_id == 0
+    fd.num_training_steps = 10  # attribute write done by vqa_cont_learner.py:211
+    fd.update_after_backward(model=None)
+    fd.update_after_step(model=None, batch_idx=3)
+    fd.update_after_new_task(model=None, dataset=None)
+    fd.update_mask()
