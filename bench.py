@@ -206,7 +206,7 @@ def run_reference_arm(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(wl, n_gpus):
@@ -219,7 +219,27 @@ def workload_config(wl, n_gpus):
 
 
 # ----------------------------------------------------------------------------- main arm
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Route everything libraries print to stdout (NCCL's version banner, warnings) to stderr so that
+    stdout carries exactly one line: the JSON result."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -409,7 +429,7 @@ def main():
         except Exception as exc:
             line["cpu_baseline"] = {"error": repr(exc)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -145,6 +145,15 @@ int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_p
                         const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
                         const float* bwd_scale, float assumed_grad_out, void* ws, void* stream);
 
+/* Gradient-norm modality importances (distillation_loss_weights.py:122-137): for every tensor of the
+ * table (one per selected layer, [B, T, D]) the per-token L2 norm over D (`torch.linalg.norm(grad,
+ * dim=-1)`, :131) summed per modality with the mask weights (:133-137), all layers in one pass.
+ * Writes per-CTA partials to `ws`; follow with mafed_distill_reduce to obtain
+ * sums[2l] = sum_text w*|g|, sums[2l+1] = sum_vision |g|, sums[2L], sums[2L+1] = token counts.
+ * shape->loss_kind is ignored. */
+int mafed_distill_token_norm_sums(const mafed_shape_t* shape, const void* const* tensor_ptrs,
+                                  const int64_t* attn_mask, void* ws, void* stream);
+
 /* The two [B, T] int64 masks the reference stores into the batch dict (distillation.py:134-144):
  * lang_mask[:, n_vis:] = attn_mask, image_mask[:, :n_vis] = 1, zeros elsewhere -- one launch, on the
  * device (the reference builds them on the CPU and copies them over, per layer). */

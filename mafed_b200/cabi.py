@@ -28,8 +28,8 @@ EXPORTS = (
     "mafed_distill_abi_version", "mafed_distill_error_string", "mafed_distill_ws_bytes",
     "mafed_distill_sums_len", "mafed_distill_out_len", "mafed_distill_fwd", "mafed_distill_scalar_stage",
     "mafed_distill_reduce", "mafed_distill_finalize", "mafed_distill_epilogue", "mafed_distill_prologue",
-    "mafed_distill_bwd", "mafed_distill_fused", "mafed_distill_modality_masks", "mafed_distill_set_variant",
-    "mafed_distill_set_tuning",
+    "mafed_distill_bwd", "mafed_distill_fused", "mafed_distill_modality_masks", "mafed_distill_token_norm_sums",
+    "mafed_distill_set_variant", "mafed_distill_set_tuning",
 )
 TUNE_NO_PDL = 15
 
@@ -98,6 +98,8 @@ def load():
         lib.mafed_distill_bwd.argtypes = [sh, pp, pp, pp, vp, vp, vp, ctypes.POINTER(ctypes.c_float), vp]
         lib.mafed_distill_fused.restype = i32
         lib.mafed_distill_fused.argtypes = [sh, pp, pp, pp, vp, vp, ctypes.c_float, vp, vp]
+        lib.mafed_distill_token_norm_sums.restype = i32
+        lib.mafed_distill_token_norm_sums.argtypes = [sh, pp, vp, vp, vp]
         lib.mafed_distill_modality_masks.restype = i32
         lib.mafed_distill_modality_masks.argtypes = [sh, vp, vp, vp, vp]
         lib.mafed_distill_set_variant.restype = i32

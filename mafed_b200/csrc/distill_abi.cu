@@ -114,7 +114,10 @@ template <typename T, int CPL, int RPI, int LOSS>
 int launch_ldg(const PathParams& p, int pass, cudaStream_t st) {
   static int occ[3] = {0, 0, 0};
   const DeviceInfo& dv = device_info();
-  if (occ[pass] == 0) {
+  if constexpr (LOSS == kLossL2Norm) {
+    if (pass != kPassFwd) return MAFED_E_ARG;  // the token-norm reduction has no backward
+    if (occ[0] == 0) occ[0] = blocks_per_sm(k_fwd_ldg<T, CPL, RPI, LOSS>, kLdgThreads, 0);
+  } else if (occ[pass] == 0) {
     occ[pass] = pass == kPassFwd   ? blocks_per_sm(k_fwd_ldg<T, CPL, RPI, LOSS>, kLdgThreads, 0)
                 : pass == kPassBwd ? blocks_per_sm(k_bwd_ldg<T, CPL, RPI, LOSS, kBackward>, kLdgThreads, 0)
                                    : blocks_per_sm(k_bwd_ldg<T, CPL, RPI, LOSS, kFused>, kLdgThreads, 0);
@@ -125,9 +128,13 @@ int launch_ldg(const PathParams& p, int pass, cudaStream_t st) {
   const long long rows_per_iter = (long long)kLdgWarps * RPI;
   const long long total = ((p.n_rows + rows_per_iter - 1) / rows_per_iter) * p.n_layers;
   const unsigned grid = (unsigned)clamp_grid((long long)dv.sm_count * per_sm, total);
-  if (pass == kPassFwd) launch_pdl(k_fwd_ldg<T, CPL, RPI, LOSS>, grid, kLdgThreads, 0, st, p);
-  else if (pass == kPassBwd) launch_pdl(k_bwd_ldg<T, CPL, RPI, LOSS, kBackward>, grid, kLdgThreads, 0, st, p);
-  else launch_pdl(k_bwd_ldg<T, CPL, RPI, LOSS, kFused>, grid, kLdgThreads, 0, st, p);
+  if constexpr (LOSS == kLossL2Norm) {
+    launch_pdl(k_fwd_ldg<T, CPL, RPI, LOSS>, grid, kLdgThreads, 0, st, p);
+  } else {
+    if (pass == kPassFwd) launch_pdl(k_fwd_ldg<T, CPL, RPI, LOSS>, grid, kLdgThreads, 0, st, p);
+    else if (pass == kPassBwd) launch_pdl(k_bwd_ldg<T, CPL, RPI, LOSS, kBackward>, grid, kLdgThreads, 0, st, p);
+    else launch_pdl(k_bwd_ldg<T, CPL, RPI, LOSS, kFused>, grid, kLdgThreads, 0, st, p);
+  }
   return (int)cudaPeekAtLastError();
 }
 
@@ -149,8 +156,10 @@ int launch_generic(const PathParams& p, int pass, cudaStream_t st) {
   const long long total = ((p.n_rows + kLdgWarps - 1) / kLdgWarps) * p.n_layers;
   const unsigned grid = (unsigned)clamp_grid((long long)dv.sm_count * 4, total);
   if (pass == kPassFwd || pass == kPassFused) launch_pdl(k_fwd_generic<T, LOSS>, grid, kLdgThreads, 0, st, p);
-  if (pass == kPassBwd || pass == kPassFused)
-    launch_pdl(k_bwd_generic<T, LOSS>, grid, kLdgThreads, 0, st, p, pass == kPassFused ? 1 : 0);
+  if constexpr (LOSS != kLossL2Norm) {
+    if (pass == kPassBwd || pass == kPassFused)
+      launch_pdl(k_bwd_generic<T, LOSS>, grid, kLdgThreads, 0, st, p, pass == kPassFused ? 1 : 0);
+  }
   return (int)cudaPeekAtLastError();
 }
 
@@ -187,7 +196,14 @@ int launch_tma(const PathParams& p, const TmaGeom& geo, int pass, cudaStream_t s
   const DeviceInfo& dv = device_info();
   const size_t dyn = (size_t)geo.stages * geo.stage_bytes;
   const int max_dyn = dv.smem_optin - 16 * 1024;
-  if (!attr[pass]) {
+  if constexpr (LOSS == kLossL2Norm) {
+    if (pass != kPassFwd) return MAFED_E_ARG;
+    if (!attr[0]) {
+      cudaError_t e = cudaFuncSetAttribute(k_fwd_tma<T, LOSS, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+      if (e != cudaSuccess) return (int)e;
+      attr[0] = true;
+    }
+  } else if (!attr[pass]) {
     cudaError_t e =
         pass == kPassFwd ? cudaFuncSetAttribute(k_fwd_tma<T, LOSS, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn)
         : pass == kPassBwd
@@ -201,9 +217,13 @@ int launch_tma(const PathParams& p, const TmaGeom& geo, int pass, cudaStream_t s
   if (mul <= 0) mul = 1;
   const unsigned grid = (unsigned)clamp_grid((long long)dv.sm_count * mul, total);
   constexpr int threads = (NCW + 1) * 32;
-  if (pass == kPassFwd) launch_pdl(k_fwd_tma<T, LOSS, NCW>, grid, threads, dyn, st, p, geo);
-  else if (pass == kPassBwd) launch_pdl(k_bwd_tma<T, LOSS, NCW, kBackward>, grid, threads, dyn, st, p, geo);
-  else launch_pdl(k_bwd_tma<T, LOSS, NCW, kFused>, grid, threads, dyn, st, p, geo);
+  if constexpr (LOSS == kLossL2Norm) {
+    launch_pdl(k_fwd_tma<T, LOSS, NCW>, grid, threads, dyn, st, p, geo);
+  } else {
+    if (pass == kPassFwd) launch_pdl(k_fwd_tma<T, LOSS, NCW>, grid, threads, dyn, st, p, geo);
+    else if (pass == kPassBwd) launch_pdl(k_bwd_tma<T, LOSS, NCW, kBackward>, grid, threads, dyn, st, p, geo);
+    else launch_pdl(k_bwd_tma<T, LOSS, NCW, kFused>, grid, threads, dyn, st, p, geo);
+  }
   return (int)cudaPeekAtLastError();
 }
 
@@ -228,10 +248,11 @@ int dispatch_typed(PathParams& p, bool vector_ok, int pass, cudaStream_t st) {
 template <typename T>
 int dispatch_loss(PathParams& p, int loss, bool vector_ok, int pass, cudaStream_t st) {
   if (loss == MAFED_LOSS_MSE) return dispatch_typed<T, MAFED_LOSS_MSE>(p, vector_ok, pass, st);
+  if (loss == kLossL2Norm) return dispatch_typed<T, kLossL2Norm>(p, vector_ok, pass, st);
   return dispatch_typed<T, MAFED_LOSS_COSINE>(p, vector_ok, pass, st);
 }
 
-int dispatch(const mafed_shape_t& sh, PathParams& p, int pass, cudaStream_t st) {
+int dispatch(const mafed_shape_t& sh, PathParams& p, int pass, cudaStream_t st, int loss_override = -1) {
   // vector path: rows are whole, 16-byte aligned chunks
   const size_t es = elem_size(sh.dtype);
   bool vector_ok = ((size_t)sh.D * es) % 16 == 0 && ((size_t)p.row_stride * es) % 16 == 0;
@@ -240,10 +261,11 @@ int dispatch(const mafed_shape_t& sh, PathParams& p, int pass, cudaStream_t st) 
   p.n_chunks = vector_ok ? (int)((size_t)sh.D * es / 16) : 0;
   p.load_policy = g_tune[kTuneLoadPolicy].load();
   p.store_policy = g_tune[kTuneStorePolicy].load();
+  const int loss = loss_override >= 0 ? loss_override : sh.loss_kind;
   switch (sh.dtype) {
-    case MAFED_F32: return dispatch_loss<float>(p, sh.loss_kind, vector_ok, pass, st);
-    case MAFED_BF16: return dispatch_loss<__nv_bfloat16>(p, sh.loss_kind, vector_ok, pass, st);
-    default: return dispatch_loss<__half>(p, sh.loss_kind, vector_ok, pass, st);
+    case MAFED_F32: return dispatch_loss<float>(p, loss, vector_ok, pass, st);
+    case MAFED_BF16: return dispatch_loss<__nv_bfloat16>(p, loss, vector_ok, pass, st);
+    default: return dispatch_loss<__half>(p, loss, vector_ok, pass, st);
   }
 }
 
@@ -328,6 +350,17 @@ int mafed_distill_fwd(const mafed_shape_t* shape, const void* const* student_ptr
   if (!ws) return MAFED_E_ARG;
   p.ws = reinterpret_cast<float*>(ws);
   return dispatch(*shape, p, kPassFwd, (cudaStream_t)stream);
+}
+
+int mafed_distill_token_norm_sums(const mafed_shape_t* shape, const void* const* tensor_ptrs, const int64_t* attn_mask,
+                                  void* ws, void* stream) {
+  PathParams p;
+  int rc = fill_params(shape, tensor_ptrs, tensor_ptrs, nullptr, attn_mask, p);
+  if (rc) return rc;
+  if (!ws) return MAFED_E_ARG;
+  p.ws = reinterpret_cast<float*>(ws);
+  p.single_input = 1;
+  return dispatch(*shape, p, kPassFwd, (cudaStream_t)stream, kLossL2Norm);
 }
 
 int mafed_distill_scalar_stage(const mafed_shape_t* shape, const mafed_weights_t* weights, int flags,

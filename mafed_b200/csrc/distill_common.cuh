@@ -10,6 +10,9 @@
 namespace mafed {
 
 constexpr int kMaxLayers = MAFED_MAX_LAYERS;
+// Third "loss": per-token L2 norm of a single tensor (no teacher), for the gradient-norm modality
+// importances of distillation_loss_weights.py:91-146.  Forward kernels only.
+constexpr int kLossL2Norm = 2;
 constexpr float kCosEps = 1e-12f;  // EPSILON of ATen's cosine_embedding_loss
 constexpr int kMaxPartials = 2048;  // upper bound on CTAs writing partial sums
 constexpr int kWsHeaderFloats = 4;  // ws[0] = number of partial blocks (as int)
@@ -34,6 +37,7 @@ struct PathParams {
   int reverse;                   // backward: walk work items last-to-first (L2 reuse after forward)
   float fixed_gout;              // fused pass: upstream gradient assumed at forward time (host value)
   int skip_if_gout_equals;       // backward fix-up: return at once when *grad_out == fixed_gout
+  int single_input;              // 1: only `s` is read (token-norm sums); the teacher table is ignored
   int load_policy;               // L2 eviction hint for student/teacher reads (CachePolicy)
   int store_policy;              // L2 eviction hint for gradient writes
 };
@@ -182,6 +186,8 @@ __device__ __forceinline__ void accumulate(const float (&a)[NE], const float (&b
     if (LOSS == MAFED_LOSS_MSE) {
       const float d = a[i] - b[i];
       x = fmaf(d, d, x);
+    } else if (LOSS == kLossL2Norm) {
+      x = fmaf(a[i], a[i], x);
     } else {
       x = fmaf(a[i], b[i], x);
       y = fmaf(a[i], a[i], y);
@@ -194,6 +200,7 @@ __device__ __forceinline__ void accumulate(const float (&a)[NE], const float (&b
 template <int LOSS>
 __device__ __forceinline__ float row_value(float x, float y, float z) {
   if (LOSS == MAFED_LOSS_MSE) return x;  // division by D happens once, in the epilogue
+  if (LOSS == kLossL2Norm) return sqrtf(x);
   const float den = sqrtf((y + kCosEps) * (z + kCosEps));
   return 1.f - x / den;
 }

@@ -63,12 +63,12 @@ __global__ void __launch_bounds__(kLdgThreads, kLdgMinBlocks) k_fwd_ldg(const __
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           const int c = pass * 32 * CPL + lane + 32 * i;
+          tv[r][i] = make_uint4(0, 0, 0, 0);
           if (w[r] != 0.f && c < p.n_chunks) {
             sv[r][i] = ldg_stream(sb + off + (long long)c * 16, p.load_policy, lpol);
-            tv[r][i] = ldg_stream(tb + off + (long long)c * 16, p.load_policy, lpol);
+            if (LOSS != kLossL2Norm) tv[r][i] = ldg_stream(tb + off + (long long)c * 16, p.load_policy, lpol);
           } else {
             sv[r][i] = make_uint4(0, 0, 0, 0);
-            tv[r][i] = make_uint4(0, 0, 0, 0);
           }
         }
       }

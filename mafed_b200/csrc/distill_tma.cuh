@@ -101,7 +101,8 @@ __device__ __forceinline__ void tma_producer(const PathParams& p, const TmaGeom&
     if (lane == 0) { mt.layer = l; mt.n_rows = n_rows; mt.row0 = row0; }
     __syncwarp();
     const uint32_t bar = smem_u32(&full[stage]);
-    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)__popc(valid) * 2u * row_bytes);
+    const bool both = !p.single_input;
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)__popc(valid) * (both ? 2u : 1u) * row_bytes);
     __syncwarp();
     const uint32_t s_dst = smem_u32(data + (size_t)stage * geo.stage_bytes);
     const uint32_t t_dst = s_dst + (uint32_t)geo.rows * row_bytes;
@@ -111,11 +112,12 @@ __device__ __forceinline__ void tma_producer(const PathParams& p, const TmaGeom&
     if (contiguous && valid == all) {
       // whole tile live: one bulk copy per tensor
       if (lane == 0) bulk_g2s(s_dst, sb, (uint32_t)n_rows * row_bytes, bar, p.load_policy, lpol);
-      if (lane == 1) bulk_g2s(t_dst, tb, (uint32_t)n_rows * row_bytes, bar, p.load_policy, lpol);
+      if (lane == 1 && both) bulk_g2s(t_dst, tb, (uint32_t)n_rows * row_bytes, bar, p.load_policy, lpol);
     } else if (w != 0.f) {
       // ragged tile: only live rows are fetched (padded text rows cost no bandwidth)
       bulk_g2s(s_dst + (uint32_t)lane * row_bytes, sb + (long long)lane * row_pitch, row_bytes, bar, p.load_policy, lpol);
-      bulk_g2s(t_dst + (uint32_t)lane * row_bytes, tb + (long long)lane * row_pitch, row_bytes, bar, p.load_policy, lpol);
+      if (both)
+        bulk_g2s(t_dst + (uint32_t)lane * row_bytes, tb + (long long)lane * row_pitch, row_bytes, bar, p.load_policy, lpol);
     }
     if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
   }
@@ -189,7 +191,7 @@ k_fwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           sv[u] = lds_128(sa + (uint32_t)(c + 32 * u) * 16u);
-          tv[u] = lds_128(ta + (uint32_t)(c + 32 * u) * 16u);
+          tv[u] = (LOSS == kLossL2Norm) ? sv[u] : lds_128(ta + (uint32_t)(c + 32 * u) * 16u);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -201,8 +203,9 @@ k_fwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
       }
       for (; c < p.n_chunks; c += 32) {
         float a[NE], b[NE];
-        Pack<T>::unpack(lds_128(sa + (uint32_t)c * 16u), a);
-        Pack<T>::unpack(lds_128(ta + (uint32_t)c * 16u), b);
+        const uint4 sv1 = lds_128(sa + (uint32_t)c * 16u);
+        Pack<T>::unpack(sv1, a);
+        Pack<T>::unpack((LOSS == kLossL2Norm) ? sv1 : lds_128(ta + (uint32_t)c * 16u), b);
         accumulate<LOSS, NE>(a, b, x, y, z);
       }
       float val;

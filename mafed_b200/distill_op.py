@@ -139,6 +139,26 @@ def modality_masks(attn_mask: torch.Tensor, n_vis: int):
     return lang, image
 
 
+def token_norm_sums(tensors: Sequence[torch.Tensor], attn_mask: torch.Tensor, n_vis: int) -> torch.Tensor:
+    """Masked per-modality sums of the per-token L2 norms of ``len(tensors)`` ``[B, T, D]`` tensors in one
+    fused pass (``distillation_loss_weights.py:122-137``).  Returns device fp64 ``[2L + 2]``:
+    ``(text sum, vision sum)`` per tensor, then ``(n_text, n_vision)``.  No host synchronisation."""
+    lib = cabi.load()
+    tensors = _prepare([t.detach() for t in tensors])
+    plan = DistillPlan(layers=list(range(len(tensors))), layer_coeffs=[1.0] * len(tensors), n_vis=n_vis)
+    ln = _Launch(tensors, tensors, attn_mask, plan)
+    L, dev = ln.n_layers, ln.device
+    with torch.cuda.device(dev):
+        stream = _stream_ptr(dev)
+        ws = torch.empty(lib.mafed_distill_ws_bytes(L), dtype=torch.uint8, device=dev)
+        sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
+        cabi.check(lib.mafed_distill_token_norm_sums(ln.shape_ref, ln.s_ptrs, ln.mask_ptr, ws.data_ptr(), stream),
+                   "mafed_distill_token_norm_sums")
+        cabi.check(lib.mafed_distill_reduce(ln.shape_ref, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream),
+                   "mafed_distill_reduce")
+    return sums
+
+
 def resolve_group(group):
     """``None``: the default process group if one is initialised with more than one rank;
     ``False``: never communicate; otherwise an explicit ``ProcessGroup``."""

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from mafed_b200 import cabi
+from mafed_b200.capture import HiddenStateCapture
 from mafed_b200.distill_op import DistillPlan, distill_loss, modality_masks
 from mafed_b200.methods.base import CLStrategy
 from mafed_b200.methods.distillation_loss_weights import DistillationWeights
@@ -28,6 +29,17 @@ try:  # W&B is optional here; the reference requires it
     import wandb as _wandb
 except Exception:  # pragma: no cover
     _wandb = None
+
+
+class _CapturedOutput:
+    """Model output whose ``hidden_states`` holds only the captured (distilled) entries."""
+
+    def __init__(self, output, hidden_states):
+        self._output = output
+        self.hidden_states = hidden_states
+
+    def __getattr__(self, name):
+        return getattr(self._output, name)
 
 
 class FeatureDistillation(CLStrategy):
@@ -89,6 +101,8 @@ class FeatureDistillation(CLStrategy):
         # gradient it bakes in is Lightning's 1/accumulate_grad_batches, checked on the device in backward
         self.single_pass = bool(kwargs.get("single_pass", True))
         self.assumed_grad_out = 1.0 / float(self.update_freq)
+        # record only the distilled hidden states with forward hooks instead of output_hidden_states=True
+        self.selective_capture = bool(kwargs.get("selective_capture", False))
         self.last_layer_losses: Optional[torch.Tensor] = None   # device [3L]: layer, then (text, vision)
         self.last_layers: List[int] = []
         self._pending_log = None
@@ -127,7 +141,13 @@ class FeatureDistillation(CLStrategy):
         do_replay = self.replay_coeff > 0 and self.task_id > 0
         loss = None
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            output = model(**batch, compute_loss=do_replay, output_hidden_states=True, return_dict=True)
+            if self.selective_capture and self.distillation_coeff != 0:
+                # keep only the distilled entries of the hidden-state tuple alive
+                with HiddenStateCapture(model, self.loss_weights.get_distillation_layers()) as cap:
+                    output = model(**batch, compute_loss=do_replay, output_hidden_states=False, return_dict=True)
+                output = _CapturedOutput(output, cap.hidden_states)
+            else:
+                output = model(**batch, compute_loss=do_replay, output_hidden_states=True, return_dict=True)
             if do_replay:
                 loss = self.replay_coeff * output.loss
             if self.distillation_coeff == 0:
@@ -187,6 +207,11 @@ class FeatureDistillation(CLStrategy):
     def _get_past_hidden_states(self, batch):
         with torch.no_grad():
             batch.pop("labels", None)
+            if self.selective_capture:
+                layers = self.loss_weights.get_distillation_layers()
+                with HiddenStateCapture(self.past_model, layers, detach=True) as cap:
+                    self.past_model(**batch, output_hidden_states=False, return_dict=True)
+                return cap.hidden_states
             states = self.past_model(**batch, output_hidden_states=True, return_dict=True).hidden_states
         return [h.detach() for h in states]
 

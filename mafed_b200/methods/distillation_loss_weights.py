@@ -155,30 +155,28 @@ class DistillationWeights:
         For every batch: gradient of the LM loss w.r.t. each selected hidden state, per-token L2
         norm, masked sums per modality; finally ``lang / (lang + image)`` of the per-token means.
         """
+        from mafed_b200.distill_op import modality_masks as device_masks, token_norm_sums
+
         model.eval()
         layers = self.get_distillation_layers()
+        L = len(layers)
         n_vis = self.num_vision_tokens
-        lang_sum = image_sum = None
-        n_lang = n_image = 0.0
+        running = None  # device fp64 [2L + 2]: per layer (text, vision) norm sums, then token counts
         for batch in dataloader:
             model.zero_grad()
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 outputs = model(**batch, compute_loss=True, output_hidden_states=True,
                                 allow_input_gradients=True, return_dict=True)
-                attn = batch["attention_mask"]
-                lang_mask, image_mask = modality_masks(attn, n_vis)
-                batch["lang_masks"], batch["image_masks"] = lang_mask, image_mask
-                states = [outputs.hidden_states[l] for l in layers]
-                grads = torch.autograd.grad(outputs.loss, states, retain_graph=False, create_graph=False)
-                norms = torch.stack([torch.linalg.norm(g, dim=-1) for g in grads])  # [L, B, T]
-                lang_now = (norms * lang_mask).sum(dim=(1, 2))
-                image_now = (norms * image_mask).sum(dim=(1, 2))
-                lang_sum = lang_now if lang_sum is None else lang_sum + lang_now
-                image_sum = image_now if image_sum is None else image_sum + image_now
-                n_lang = n_lang + lang_mask.sum()
-                n_image = n_image + image_mask.sum()
-        lang_imp = lang_sum / n_lang
-        image_imp = image_sum / n_image
+            attn = batch["attention_mask"]
+            batch["lang_masks"], batch["image_masks"] = device_masks(attn, n_vis)
+            states = [outputs.hidden_states[l] for l in layers]
+            grads = torch.autograd.grad(outputs.loss, states, retain_graph=False, create_graph=False)
+            # one fused pass over all L gradients instead of L x (norm, 2 masked sums)
+            now = token_norm_sums(grads, attn, n_vis)
+            running = now if running is None else running + now
+        sums = running[: 2 * L].reshape(L, 2)
+        lang_imp = (sums[:, 0] / running[2 * L]).float()
+        image_imp = (sums[:, 1] / running[2 * L + 1]).float()
         model.zero_grad()
         return lang_imp / (lang_imp + image_imp)
 

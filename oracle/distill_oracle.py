@@ -282,3 +282,30 @@ def make_inputs(n_tuple: int, bsz: int, txt: int, dim: int, n_vis: int = 256, dt
             valid = 1 + (7 * b) % txt
             am[b, : txt - valid] = 0  # left padding: zeros first, valid tokens on the right
     return students, teachers, am
+
+
+# --------------------------------------------------------------------------- adaptive importances
+def adaptive_importances(model, batches, layers, n_vis):
+    """distillation_loss_weights.py:91-146 restated: per batch, gradient of the LM loss w.r.t. each selected
+    hidden state, per-token L2 norm (:131), masked sums per modality (:133-137); then per-token means and
+    lang / (lang + image) (:142-144)."""
+    model.eval()
+    lang = torch.zeros(len(layers))
+    image = torch.zeros(len(layers))
+    n_lang = n_image = 0.0
+    for batch in batches:
+        model.zero_grad()
+        out = model(**batch, compute_loss=True, output_hidden_states=True, allow_input_gradients=True,
+                    return_dict=True)
+        lang_mask, image_mask = build_masks(batch["attention_mask"], n_vis)
+        for i, layer in enumerate(layers):
+            grad = torch.autograd.grad(out.loss, out.hidden_states[layer], retain_graph=True)[0]
+            norm = torch.linalg.norm(grad, dim=-1)
+            lang[i] += (norm * lang_mask).sum()
+            image[i] += (norm * image_mask).sum()
+        n_lang += lang_mask.sum()
+        n_image += image_mask.sum()
+    lang = lang / n_lang
+    image = image / n_image
+    model.zero_grad()
+    return lang / (lang + image)
