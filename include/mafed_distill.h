@@ -145,6 +145,25 @@ int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_p
                         const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
                         const float* bwd_scale, float assumed_grad_out, void* ws, void* stream);
 
+/* ---- batch-sharded step without NCCL on the critical path: peer-memory communicator ----------------
+ * One process per GPU of one NVLink/NVSwitch box.  Each rank creates a small mailbox (cudaMalloc +
+ * CUDA IPC handle), the handles are exchanged out of band (torch.distributed all_gather in
+ * mafed_b200/comm.py) and every rank maps its peers' mailboxes.  mafed_distill_scalar_stage_comm is
+ * mafed_distill_scalar_stage with a one-shot SUM-allreduce of the selected part of the sums vector
+ * (MAFED_COMM_SUMS: [0, 2L), MAFED_COMM_COUNTS: [2L, 2L+2)) performed inside the same kernel with NVLink
+ * peer stores + flags, after REDUCE/COUNTS and before LOSSES/SCALE.  Results are bit-identical on all
+ * ranks; spins are bounded (mafed_comm_status reports a timeout), `sums` must not be NULL. */
+typedef struct mafed_comm mafed_comm_t;
+enum { MAFED_COMM_SUMS = 1, MAFED_COMM_COUNTS = 2 };
+int mafed_comm_handle_bytes(void);
+int mafed_comm_create(int world, int rank, void* ipc_handle_out, mafed_comm_t** out);
+int mafed_comm_connect(mafed_comm_t* comm, const void* all_handles /* world x handle_bytes, rank order */);
+int mafed_comm_status(mafed_comm_t* comm, int* status_out /* 0 ok, 1 a peer timed out */);
+int mafed_comm_destroy(mafed_comm_t* comm);
+int mafed_distill_scalar_stage_comm(const mafed_shape_t* shape, const mafed_weights_t* weights, int flags,
+                                    const int64_t* attn_mask, const void* ws, double* sums, float* out,
+                                    float* bwd_scale, mafed_comm_t* comm, int comm_what, void* stream);
+
 /* Gradient-norm modality importances (distillation_loss_weights.py:122-137): for every tensor of the
  * table (one per selected layer, [B, T, D]) the per-token L2 norm over D (`torch.linalg.norm(grad,
  * dim=-1)`, :131) summed per modality with the mask weights (:133-137), all layers in one pass.

@@ -29,8 +29,10 @@ EXPORTS = (
     "mafed_distill_sums_len", "mafed_distill_out_len", "mafed_distill_fwd", "mafed_distill_scalar_stage",
     "mafed_distill_reduce", "mafed_distill_finalize", "mafed_distill_epilogue", "mafed_distill_prologue",
     "mafed_distill_bwd", "mafed_distill_fused", "mafed_distill_modality_masks", "mafed_distill_token_norm_sums",
-    "mafed_distill_set_variant", "mafed_distill_set_tuning",
+    "mafed_distill_set_variant", "mafed_distill_set_tuning", "mafed_distill_scalar_stage_comm",
+    "mafed_comm_handle_bytes", "mafed_comm_create", "mafed_comm_connect", "mafed_comm_status", "mafed_comm_destroy",
 )
+COMM_SUMS, COMM_COUNTS = 1, 2
 TUNE_NO_PDL = 15
 
 
@@ -98,6 +100,17 @@ def load():
         lib.mafed_distill_bwd.argtypes = [sh, pp, pp, pp, vp, vp, vp, ctypes.POINTER(ctypes.c_float), vp]
         lib.mafed_distill_fused.restype = i32
         lib.mafed_distill_fused.argtypes = [sh, pp, pp, pp, vp, vp, ctypes.c_float, vp, vp]
+        lib.mafed_distill_scalar_stage_comm.restype = i32
+        lib.mafed_distill_scalar_stage_comm.argtypes = [sh, wt, i32, vp, vp, vp, vp, vp, vp, i32, vp]
+        lib.mafed_comm_handle_bytes.restype = i32
+        lib.mafed_comm_create.restype = i32
+        lib.mafed_comm_create.argtypes = [i32, i32, ctypes.c_char_p, ctypes.POINTER(vp)]
+        lib.mafed_comm_connect.restype = i32
+        lib.mafed_comm_connect.argtypes = [vp, ctypes.c_char_p]
+        lib.mafed_comm_status.restype = i32
+        lib.mafed_comm_status.argtypes = [vp, ctypes.POINTER(i32)]
+        lib.mafed_comm_destroy.restype = i32
+        lib.mafed_comm_destroy.argtypes = [vp]
         lib.mafed_distill_token_norm_sums.restype = i32
         lib.mafed_distill_token_norm_sums.argtypes = [sh, pp, vp, vp, vp]
         lib.mafed_distill_modality_masks.restype = i32

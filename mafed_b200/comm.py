@@ -1,0 +1,79 @@
+"""Peer-memory communicator for the batch-sharded step (one process per GPU, one NVLink box).
+
+`torch.distributed` is only the plumbing here: it carries the 64-byte CUDA IPC handles once, at set-up.
+After that the per-step exchange (<= 2L+2 doubles) happens inside the single-CTA scalar-stage kernel with
+NVLink peer stores and flags (``csrc/distill_comm.cuh``) -- no NCCL call and no extra launch on the step's
+critical path.  If the ranks are not on one host, or a mailbox cannot be mapped, every rank falls back to
+the NCCL allreduce together.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import socket
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import cabi
+
+_cache: Dict[tuple, Optional["PeerComm"]] = {}
+
+
+class PeerComm:
+    def __init__(self, handle: ctypes.c_void_p, world: int, rank: int):
+        self.handle, self.world, self.rank = handle, world, rank
+
+    def status(self) -> int:
+        """0 = ok, 1 = a peer did not arrive within the spin bound (synchronises the device)."""
+        out = ctypes.c_int(0)
+        cabi.check(cabi.load().mafed_comm_status(self.handle, ctypes.byref(out)), "mafed_comm_status")
+        return out.value
+
+    def close(self):
+        if self.handle:
+            cabi.load().mafed_comm_destroy(self.handle)
+            self.handle = None
+
+
+def _build(group) -> Optional[PeerComm]:
+    lib = cabi.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world > 16:
+        return None
+    n = lib.mafed_comm_handle_bytes()
+    buf = ctypes.create_string_buffer(n)
+    handle = ctypes.c_void_p()
+    ok = lib.mafed_comm_create(world, rank, buf, ctypes.byref(handle)) == 0
+    infos = [None] * world
+    dist.all_gather_object(infos, (socket.gethostname(), bytes(buf.raw) if ok else None), group=group)
+    same_host = len({h for h, _ in infos}) == 1
+    if ok and same_host and all(b is not None for _, b in infos):
+        ok = lib.mafed_comm_connect(handle, b"".join(b for _, b in infos)) == 0
+    else:
+        ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(ok), group=group)   # also a barrier: every mailbox is zeroed and mapped
+    if not all(flags):
+        if handle:
+            lib.mafed_comm_destroy(handle)
+        return None
+    return PeerComm(handle, world, rank)
+
+
+def get_peer_comm(group=None) -> Optional[PeerComm]:
+    """The communicator of `group` (default group if None) on the current device; None -> use NCCL."""
+    if os.environ.get("MAFED_B200_DIST", "peer").lower() == "nccl":
+        return None
+    key = (id(group) if group is not None else 0, torch.cuda.current_device())
+    if key not in _cache:
+        _cache[key] = _build(group)
+    return _cache[key]
+
+
+def reset():
+    for c in _cache.values():
+        if c is not None:
+            c.close()
+    _cache.clear()

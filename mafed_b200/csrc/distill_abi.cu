@@ -293,10 +293,48 @@ int fill_params(const mafed_shape_t* shape, const void* const* student_ptrs, con
   return 0;
 }
 
+}  // namespace
+}  // namespace mafed
+
+// Host handle of the peer-memory communicator (see distill_comm.cuh).
+struct mafed_comm {
+  int world = 0;
+  int rank = 0;
+  void* local = nullptr;
+  void* peers[mafed::kCommMaxRanks] = {};
+};
+
+namespace mafed {
+namespace {
+
+CommDev comm_dev(const mafed_comm* c) {
+  CommDev d;
+  memset(&d, 0, sizeof(d));
+  if (c == nullptr || c->world <= 1) return d;
+  d.world = c->world;
+  d.rank = c->rank;
+  for (int r = 0; r < c->world; ++r) {
+    d.data[r] = reinterpret_cast<double*>(c->peers[r]);
+    d.flags[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->peers[r]) + kCommDataBytes);
+  }
+  char* tail = reinterpret_cast<char*>(c->local) + kCommDataBytes + kCommFlagBytes;
+  d.epoch = reinterpret_cast<unsigned long long*>(tail);
+  d.status = reinterpret_cast<int*>(tail + 16);
+  return d;
+}
+
 int launch_scalar_stage(const mafed_shape_t& sh, const mafed_weights_t* w, int flags, const int64_t* mask,
-                        const void* ws, double* sums, float* out, float* bwd_scale, cudaStream_t st) {
+                        const void* ws, double* sums, float* out, float* bwd_scale, cudaStream_t st,
+                        const mafed_comm* comm = nullptr, int comm_what = 0) {
   EpiParams e;
   memset(&e, 0, sizeof(e));
+  e.comm = comm_dev(comm);
+  if (e.comm.world > 1) {
+    const int L2 = 2 * sh.n_layers;
+    if (comm_what == (MAFED_COMM_SUMS | MAFED_COMM_COUNTS)) { e.comm_first = 0; e.comm_count = L2 + 2; }
+    else if (comm_what == MAFED_COMM_SUMS) { e.comm_first = 0; e.comm_count = L2; }
+    else if (comm_what == MAFED_COMM_COUNTS) { e.comm_first = L2; e.comm_count = 2; }
+  }
   e.ws = reinterpret_cast<const float*>(ws);
   e.mask = mask;
   e.sums = sums;
@@ -378,6 +416,73 @@ int mafed_distill_scalar_stage(const mafed_shape_t* shape, const mafed_weights_t
   const bool only_writes = (flags & (MAFED_STAGE_LOSSES | MAFED_STAGE_SCALE)) == 0;
   if ((reads_sums || only_writes) && !sums) return MAFED_E_ARG;
   return launch_scalar_stage(*shape, weights, flags, attn_mask, ws, sums, out, bwd_scale, (cudaStream_t)stream);
+}
+
+int mafed_distill_scalar_stage_comm(const mafed_shape_t* shape, const mafed_weights_t* weights, int flags,
+                                    const int64_t* attn_mask, const void* ws, double* sums, float* out,
+                                    float* bwd_scale, mafed_comm_t* comm, int comm_what, void* stream) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if ((flags & MAFED_STAGE_REDUCE) && !ws) return MAFED_E_ARG;
+  if ((flags & MAFED_STAGE_COUNTS) && needs_mask(*shape) && !attn_mask) return MAFED_E_ARG;
+  if ((flags & (MAFED_STAGE_LOSSES | MAFED_STAGE_SCALE)) && !weights) return MAFED_E_ARG;
+  if ((flags & MAFED_STAGE_LOSSES) && !out) return MAFED_E_ARG;
+  if ((flags & MAFED_STAGE_SCALE) && !bwd_scale) return MAFED_E_ARG;
+  if (!sums) return MAFED_E_ARG;  // the distributed sequence always carries the sums vector between stages
+  if (comm != nullptr && (comm->world > kCommMaxRanks || comm_what < 0 || comm_what > 3)) return MAFED_E_ARG;
+  return launch_scalar_stage(*shape, weights, flags, attn_mask, ws, sums, out, bwd_scale, (cudaStream_t)stream, comm,
+                             comm_what);
+}
+
+int mafed_comm_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int mafed_comm_create(int world, int rank, void* ipc_handle_out, mafed_comm_t** out) {
+  if (world < 1 || world > kCommMaxRanks || rank < 0 || rank >= world || !ipc_handle_out || !out) return MAFED_E_ARG;
+  mafed_comm* c = new mafed_comm();
+  c->world = world;
+  c->rank = rank;
+  cudaError_t e = cudaMalloc(&c->local, kCommMailboxBytes);
+  if (e == cudaSuccess) e = cudaMemset(c->local, 0, kCommMailboxBytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->local);
+  if (e != cudaSuccess) {
+    if (c->local) cudaFree(c->local);
+    delete c;
+    return (int)e;
+  }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  c->peers[rank] = c->local;
+  *out = c;
+  return 0;
+}
+
+int mafed_comm_connect(mafed_comm_t* c, const void* all_handles) {
+  if (!c || !all_handles) return MAFED_E_ARG;
+  const char* hs = reinterpret_cast<const char*>(all_handles);
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs + (size_t)r * sizeof(h), sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&c->peers[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+int mafed_comm_status(mafed_comm_t* c, int* status_out) {
+  if (!c || !status_out) return MAFED_E_ARG;
+  const char* tail = reinterpret_cast<const char*>(c->local) + kCommDataBytes + kCommFlagBytes;
+  return (int)cudaMemcpy(status_out, tail + 16, sizeof(int), cudaMemcpyDeviceToHost);
+}
+
+int mafed_comm_destroy(mafed_comm_t* c) {
+  if (!c) return 0;
+  for (int r = 0; r < c->world; ++r)
+    if (r != c->rank && c->peers[r]) cudaIpcCloseMemHandle(c->peers[r]);
+  if (c->local) cudaFree(c->local);
+  delete c;
+  return 0;
 }
 
 int mafed_distill_reduce(const mafed_shape_t* shape, const int64_t* attn_mask, const void* ws, double* sums,

@@ -6,6 +6,7 @@
 //   finalize  (losses + scale from given sums)       after the allreduce
 //   prologue  (counts + scale)                       before a fused single-pass step
 #pragma once
+#include "distill_comm.cuh"
 #include "distill_common.cuh"
 
 namespace mafed {
@@ -26,6 +27,9 @@ struct EpiParams {
   int D;
   int loss_kind;
   int flags;
+  int comm_first;         // range of the sums vector to allreduce over the peer mailboxes
+  int comm_count;         // (0 = no communication)
+  CommDev comm;
   mafed_weights_t w;
 };
 
@@ -84,6 +88,8 @@ __global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant_
     s_sums[2 * L + threadIdx.x] = p.sums[2 * L + threadIdx.x];
   }
   __syncthreads();
+  // batch-sharded step: combine this rank's sums / counts with its peers' over NVLink, in this kernel
+  if (p.comm.world > 1 && p.comm_count > 0) peer_allreduce(p.comm, s_sums + p.comm_first, p.comm_count);
   if (p.sums != nullptr) {
     if (p.flags & kEpiReduce)
       for (int i = threadIdx.x; i < 2 * L; i += kEpiThreads) p.sums[i] = s_sums[i];

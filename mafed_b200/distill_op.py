@@ -26,6 +26,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import cabi
+from .comm import get_peer_comm
 
 _DTYPES = {torch.float32: cabi.F32, torch.bfloat16: cabi.BF16, torch.float16: cabi.F16}
 
@@ -193,7 +194,15 @@ def distill_forward(students, teachers, attn_mask, plan: DistillPlan, group=None
                    "mafed_distill_fwd")
         w = ctypes.byref(plan.weights())
         distributed, pg = resolve_group(group)
-        if distributed:
+        peer = get_peer_comm(pg) if distributed else None
+        if peer is not None:
+            # reduce + counts + NVLink peer allreduce + losses + scale: one launch, no NCCL call
+            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
+            every = cabi.STAGE_REDUCE | cabi.STAGE_COUNTS | cabi.STAGE_LOSSES | cabi.STAGE_SCALE
+            cabi.check(lib.mafed_distill_scalar_stage_comm(
+                ln.shape_ref, w, every, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), out.data_ptr(),
+                bwd_scale.data_ptr(), peer.handle, cabi.COMM_SUMS | cabi.COMM_COUNTS, stream), "scalar_stage_comm")
+        elif distributed:
             sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
             cabi.check(lib.mafed_distill_reduce(ln.shape_ref, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream),
                        "mafed_distill_reduce")
@@ -233,6 +242,20 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
         ws, out, bwd_scale = ln.alloc_scalars(lib)
         w = ctypes.byref(plan.weights())
         distributed, pg = resolve_group(group)
+        peer = get_peer_comm(pg) if distributed else None
+        if peer is not None:
+            # same three launches as the single-GPU step; the two exchanges ride inside the scalar stages
+            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
+            cabi.check(lib.mafed_distill_scalar_stage_comm(
+                ln.shape_ref, w, cabi.STAGE_COUNTS | cabi.STAGE_SCALE, ln.mask_ptr, None, sums.data_ptr(), None,
+                bwd_scale.data_ptr(), peer.handle, cabi.COMM_COUNTS, stream), "prologue_comm")
+            cabi.check(lib.mafed_distill_fused(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr,
+                                               bwd_scale.data_ptr(), fixed, ws.data_ptr(), stream),
+                       "mafed_distill_fused")
+            cabi.check(lib.mafed_distill_scalar_stage_comm(
+                ln.shape_ref, w, cabi.STAGE_REDUCE | cabi.STAGE_LOSSES, None, ws.data_ptr(), sums.data_ptr(),
+                out.data_ptr(), None, peer.handle, cabi.COMM_SUMS, stream), "epilogue_comm")
+            return out, bwd_scale, ln
         if distributed:
             sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
             cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_COUNTS, ln.mask_ptr, None,

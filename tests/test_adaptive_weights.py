@@ -33,6 +33,31 @@ def test_oracle_importances_match_reference():
     np.testing.assert_allclose(imp.numpy(), z["importances"], rtol=1e-6)
 
 
+def _torch_importances(model, batches):
+    """distillation_loss_weights.py:91-146 in plain torch ops on the batches' device."""
+    lang = image = None
+    n_lang = n_image = 0.0
+    for batch in batches:
+        batch = dict(batch)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(**batch, compute_loss=True, output_hidden_states=True, allow_input_gradients=True)
+            am = batch["attention_mask"]
+            B, txt = am.shape
+            lm = torch.zeros(B, N_VIS + txt, dtype=am.dtype, device=am.device); lm[:, N_VIS:] = am
+            im = torch.zeros_like(lm); im[:, :N_VIS] = 1
+            la, ia = [], []
+            for l in range(L):
+                g = torch.autograd.grad(out.loss, out.hidden_states[l], retain_graph=True)[0]
+                n = torch.linalg.norm(g, dim=-1)
+                la.append((n * lm).sum()); ia.append((n * im).sum())
+            la, ia = torch.stack(la), torch.stack(ia)
+            lang = la if lang is None else lang + la
+            image = ia if image is None else image + ia
+            n_lang = n_lang + lm.sum(); n_image = n_image + im.sum()
+    lang = lang / n_lang; image = image / n_image
+    return lang / (lang + image)
+
+
 @pytest.mark.gpu
 def test_compute_adaptive_weights_on_gpu_matches_reference():
     from mafed_b200.methods import DistillationWeights
@@ -41,16 +66,21 @@ def test_compute_adaptive_weights_on_gpu_matches_reference():
     cuda_batches = [{k: v.cuda() for k, v in b.items()} for b in batches]
     dw = DistillationWeights("adaptive", "equal", num_hidden_layers=L, distillation_layer=None, num_vision_tokens=N_VIS)
     imp = dw.compute_adaptive_weights(model, [dict(b) for b in cuda_batches])
-    np.testing.assert_allclose(imp.cpu().numpy(), z["importances"], rtol=1e-5)
+    # (a) the reference's algorithm in plain torch on the same device under the same autocast: tight
+    want = _torch_importances(model, cuda_batches)
+    np.testing.assert_allclose(imp.cpu().numpy(), want.cpu().numpy(), rtol=1e-5)
+    # (b) the CPU golden from the unmodified reference ran the model in fp32 (autocast("cuda") is inert on
+    # CPU tensors); on the GPU the model's matmuls run in bf16, hence the bf16 tolerance
+    np.testing.assert_allclose(imp.cpu().numpy(), z["importances"], rtol=2e-3)
     b0 = dict(cuda_batches[0])
     dw.compute_adaptive_weights(model, [b0])
     assert "lang_masks" in b0 and "image_masks" in b0          # side effect kept (:115,121)
     # running average over tasks (:62-69) and the host table the kernels read
     dw.update_weights(model, [dict(b) for b in cuda_batches], 0)
-    np.testing.assert_allclose(dw.lang_coeff.cpu().numpy(), z["after_task0"], rtol=1e-5)
+    np.testing.assert_allclose(dw.lang_coeff.cpu().numpy(), z["after_task0"], rtol=2e-3)
     dw.update_weights(model, [dict(b) for b in cuda_batches[:1]], 1)
-    np.testing.assert_allclose(dw.lang_coeff.cpu().numpy(), z["after_task1"], rtol=1e-5)
-    assert dw.kernel_tables()[2] == pytest.approx([float(x) for x in z["after_task1"]], rel=1e-5)
+    np.testing.assert_allclose(dw.lang_coeff.cpu().numpy(), z["after_task1"], rtol=2e-3)
+    assert dw.kernel_tables()[2] == pytest.approx([float(x) for x in dw.lang_coeff.cpu()], rel=1e-6)
 
 
 @pytest.mark.gpu

@@ -11,9 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_sharded_equals_full_batch_nccl():
+@pytest.mark.parametrize("path", ["peer", "nccl"])
+def test_sharded_equals_full_batch(path):
     n = min(torch.cuda.device_count(), 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "multirank_check.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, MAFED_B200_DIST=path)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

@@ -51,6 +51,14 @@ def main():
         ok &= good
         print(f"rank {rank}/{world} {dtype} {loss} {modality} single_pass={single_pass}: loss err {e_loss:.2e} "
               f"grad err {e_grad:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    from mafed_b200.comm import get_peer_comm
+    peer = get_peer_comm(None)
+    mode = "nccl" if peer is None else "peer-memory"
+    if peer is not None:
+        ok &= peer.status() == 0
+    if os.environ.get("MAFED_B200_DIST", "peer") == "peer":
+        ok &= peer is not None          # on one NVLink box the mailboxes must map
+    print(f"rank {rank}: exchange path = {mode}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
