@@ -374,6 +374,10 @@ def main():
     value = units_per_step / (ms_per_step * 1e-3)
 
     peak, peak_src = peaks()
+    peer_path = False
+    if world > 1:
+        from mafed_b200.comm import get_peer_comm
+        peer_path = get_peer_comm(None) is not None
     row_bytes = D * esize
     per_gpu_units = B * T * n_sel
     gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
@@ -411,7 +415,11 @@ def main():
                               "frac_of_nominal_8000": gbs(fwd_bytes + bwd_bytes, two_ms) / 8000.0,
                               "bytes_per_unit": 5 * row_bytes},
         },
-        "gpu_launches": args.steps * (4 if world == 1 else 6),
+        # one-pass step: prologue, fused kernel, epilogue, backward fix-up; the NVLink peer exchange rides inside
+        # the two scalar stages, the NCCL fallback adds a counts kernel and a reduce kernel
+        "gpu_launches": args.steps * (4 if (world == 1 or peer_path) else 6),
+        "exchange": "none" if world == 1 else ("nvlink peer-memory mailboxes inside the scalar-stage kernels"
+                                               if peer_path else "nccl allreduce"),
         "loss": float(loss.detach()),
     }
     line["clocks"] = sampler.summary()
