@@ -39,6 +39,15 @@ N_VIS = 256
 RECIPE = dict(modality="balanced", layer_strategy="discounted", loss="mse", gamma=0.5)  # scripts/run_seed42.sh:74-93
 
 
+def measured_traffic(wl):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(wl, {}).get("fused_kernel_dram_bytes")
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -249,6 +258,7 @@ def main():
     ap.add_argument("--variant", default="default", choices=["default", "ldg", "tma"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -334,6 +344,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    host_us = {}
+
     def api_loop(single_pass):
         fd.single_pass = single_pass
         for _ in range(args.warmup):
@@ -342,10 +354,12 @@ def main():
         sampler = ClockSampler(local_rank)
         sync_all()
         with sampler:
+            t0 = time.perf_counter()
             e0.record()
             for _ in range(args.steps):
                 loss = api_step()
             e1.record()
+            host_us[single_pass] = (time.perf_counter() - t0) / args.steps * 1e6   # CPU time to enqueue one step
             sync_all()
         return e0.elapsed_time(e1), sampler, loss
 
@@ -394,13 +408,14 @@ def main():
                 "token*layer; upstream gradient checked on the device in backward)",
         "roofline": {"bound": "hbm", "kernel": "k_bwd_* <kFused> (+ prologue/epilogue scalar stages): 2 reads + 1 write",
                      "achieved": gbs(fused_bytes, fused_ms), "peak": peak, "unit": "GB/s",
-                     "frac": gbs(fused_bytes, fused_ms) / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": gbs(fused_bytes, fused_ms) / peak, "traffic": measured_traffic(wl), "peak_source": peak_src,
                      "bytes_per_launch": fused_bytes, "bytes_per_unit": 3 * row_bytes, "ms_per_launch": fused_ms,
                      "fixup_launch_ms": fixup_ms},
         "roofline_step": {"achieved": gbs(fused_bytes, ms_per_step), "peak": peak, "unit": "GB/s",
                           "frac": gbs(fused_bytes, ms_per_step) / peak,
                           "frac_of_nominal_8000": gbs(fused_bytes, ms_per_step) / 8000.0, "bytes_per_unit": 3 * row_bytes},
         "kernel_value": units_per_step / (one_raw_ms / args.steps * 1e-3),
+        "host_us_per_step": host_us.get(True),
         "two_pass": {
             "note": "north_star's two-kernel form (fused forward, then fused backward): 5*D*e bytes per token*layer",
             "value": units_per_step / (two_ms * 1e-3), "ms_per_step": two_ms,
@@ -425,6 +440,11 @@ def main():
     line["clocks"] = sampler.summary()
 
     # ---- (2) end to end with HOST buffers (pinned): H2D inputs, step, D2H gradients + loss
+    if world == 1 and not args.no_other_workloads:
+        try:
+            line["other_workloads"] = other_workloads(wl, device, peak)
+        except Exception as exc:
+            line["other_workloads"] = {"error": repr(exc)}
     if not args.no_e2e:
         try:
             line["e2e"] = run_e2e(args, fd, st, te, am, device, world, units_per_step)
@@ -441,6 +461,46 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def other_workloads(skip, device, peak, steps=40, warmup=5):
+    """The other BASELINE.json configurations that fit one GPU, through the public API (one-pass step):
+    tokens*layers/s and the step's algorithmic GB/s.  Informational; the headline stays `value`."""
+    out = {}
+    for wl in ("C2", "C3", "C1"):
+        if wl == skip:
+            continue
+        desc, n_tuple, n_sel, B, txt, D, dt = WORKLOADS[wl]
+        st, te, am = make_device_inputs(wl, 0, device)
+        fd = make_method(n_sel)
+        fd.past_model = lambda **kw: Out(tuple(te))
+        leaves = [s.detach().requires_grad_(True) for s in st]
+
+        def step():
+            for s in leaves:
+                s.grad = None
+            loss = fd.distill(Out(tuple(leaves)), {"attention_mask": am})
+            loss.backward()
+
+        for _ in range(warmup):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        units = B * (N_VIS + txt) * n_sel
+        esize = torch.finfo(torch_dtype(dt)).bits // 8
+        gbs = 3 * D * esize * units / (ms * 1e-3) / 1e9
+        out[wl] = {"workload": desc, "value": units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "step_gbs": gbs,
+                   "frac": gbs / peak, "bytes_per_unit": 3 * D * esize,
+                   "note": "L2-assisted: student+teacher+gradient = 234 MB vs 126 MB L2" if wl == "C1" else ""}
+        del st, te, leaves, fd
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_e2e(args, fd, st, te, am, device, world, units_per_step):

@@ -135,10 +135,7 @@ def check(rc: int, what: str):
 
 def ptr_array(ptrs):
     """Host array of device pointers (``const void* const*``)."""
-    arr = (ctypes.c_void_p * len(ptrs))()
-    for i, p in enumerate(ptrs):
-        arr[i] = p
-    return arr
+    return (ctypes.c_void_p * len(ptrs))(*ptrs)
 
 
 def make_shape(n_layers, B, T, n_vis, D, dtype, loss_kind, cls=False):

@@ -57,8 +57,33 @@ class DistillPlan:
         return self._weights
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream_ptr(device) -> int:
+    """cudaStream_t of torch's current stream on `device` (fast path avoids building a Stream object)."""
+    if _raw_stream is not None and device.index is not None:
+        return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` that costs nothing when `dev` is already current (the usual case)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        same = _raw_device is not None and device.index is not None and _raw_device() == device.index
+        self.ctx = None if same else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -72,6 +97,17 @@ def _prepare(tensors: Sequence[torch.Tensor]):
     return [t if t.is_contiguous() else t.contiguous() for t in tensors]
 
 
+class _DevicePtr:
+    """A raw device address inside a torch allocation that it keeps alive (``.data_ptr()`` like a tensor)."""
+    __slots__ = ("owner", "ptr")
+
+    def __init__(self, owner, ptr):
+        self.owner, self.ptr = owner, ptr
+
+    def data_ptr(self):
+        return self.ptr
+
+
 class _Launch:
     """Geometry + pointer tables of one step; keeps the tensors alive until the kernels are queued."""
 
@@ -82,14 +118,16 @@ class _Launch:
             raise TypeError(f"unsupported hidden-state dtype {s0.dtype} (float32, bfloat16, float16)")
         if s0.dim() != 3:
             raise ValueError("hidden states must be [B, T, D]")
-        self.B, self.T, self.D = s0.shape
-        for s, t in zip(students, teachers):
-            if s.shape != s0.shape or t.shape != s0.shape:
-                raise ValueError("all selected hidden states must share one [B, T, D] shape")
-            if s.dtype != s0.dtype or t.dtype != s0.dtype or t.device != s0.device:
-                raise ValueError("student / teacher dtype or device mismatch")
-        self.device = s0.device
-        self.dtype = s0.dtype
+        shape, dtype, device = s0.shape, s0.dtype, s0.device
+        self.B, self.T, self.D = shape
+        for group in (students, teachers):
+            for t in group:
+                if t.shape != shape:
+                    raise ValueError("all selected hidden states must share one [B, T, D] shape")
+                if t.dtype != dtype or t.device != device:
+                    raise ValueError("student / teacher dtype or device mismatch")
+        self.device = device
+        self.dtype = dtype
         n_vis = plan.n_vis
         if plan.cls:
             self.mask = None
@@ -114,11 +152,14 @@ class _Launch:
         self.mask_ptr = self.mask.data_ptr() if self.mask is not None else None
 
     def alloc_scalars(self, lib):
+        """(workspace, out, bwd_scale): the partial-sum workspace and the scale table share one scratch
+        allocation; `bwd_scale` is returned as a `_DevicePtr` view that keeps the scratch alive."""
         L, dev = self.n_layers, self.device
-        ws = torch.empty(lib.mafed_distill_ws_bytes(L), dtype=torch.uint8, device=dev)
+        ws_bytes = (lib.mafed_distill_ws_bytes(L) + 255) & ~255
+        scratch = torch.empty(ws_bytes + 8 * L, dtype=torch.uint8, device=dev)
         out = torch.empty(1 + 3 * L, dtype=torch.float32, device=dev)
-        bwd_scale = torch.empty(2 * L, dtype=torch.float32, device=dev)
-        return ws, out, bwd_scale
+        base = scratch.data_ptr()
+        return _DevicePtr(scratch, base), out, _DevicePtr(scratch, base + ws_bytes)
 
 
 def modality_masks(attn_mask: torch.Tensor, n_vis: int):
@@ -130,7 +171,7 @@ def modality_masks(attn_mask: torch.Tensor, n_vis: int):
     B, txt = am.shape
     both = torch.empty((2, B, n_vis + txt), dtype=torch.int64, device=am.device)
     shape = cabi.make_shape(1, B, n_vis + txt, n_vis, 1, cabi.F32, cabi.LOSS_MSE)
-    with torch.cuda.device(am.device):
+    with _on_device(am.device):
         cabi.check(lib.mafed_distill_modality_masks(ctypes.byref(shape), am.data_ptr(), both[0].data_ptr(),
                                                     both[1].data_ptr(), _stream_ptr(am.device)),
                    "mafed_distill_modality_masks")
@@ -149,7 +190,7 @@ def token_norm_sums(tensors: Sequence[torch.Tensor], attn_mask: torch.Tensor, n_
     plan = DistillPlan(layers=list(range(len(tensors))), layer_coeffs=[1.0] * len(tensors), n_vis=n_vis)
     ln = _Launch(tensors, tensors, attn_mask, plan)
     L, dev = ln.n_layers, ln.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         stream = _stream_ptr(dev)
         ws = torch.empty(lib.mafed_distill_ws_bytes(L), dtype=torch.uint8, device=dev)
         sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
@@ -187,7 +228,7 @@ def distill_forward(students, teachers, attn_mask, plan: DistillPlan, group=None
     lib = cabi.load()
     ln = _Launch(students, teachers, attn_mask, plan)
     L, dev = ln.n_layers, ln.device
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         stream = _stream_ptr(dev)
         ws, out, bwd_scale = ln.alloc_scalars(lib)
         cabi.check(lib.mafed_distill_fwd(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, ln.mask_ptr, ws.data_ptr(), stream),
@@ -223,7 +264,7 @@ def distill_backward(ln: _Launch, grads: Sequence[Optional[torch.Tensor]], bwd_s
     lib = cabi.load()
     g_ptrs = cabi.ptr_array([g.data_ptr() if g is not None else None for g in grads])
     skip = ctypes.byref(ctypes.c_float(skip_if_equals)) if skip_if_equals is not None else None
-    with torch.cuda.device(ln.device):
+    with _on_device(ln.device):
         cabi.check(lib.mafed_distill_bwd(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr,
                                          bwd_scale.data_ptr(), grad_out.data_ptr() if grad_out is not None else None,
                                          skip, _stream_ptr(ln.device)), "mafed_distill_bwd")
@@ -237,7 +278,7 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
     L, dev = ln.n_layers, ln.device
     fixed = float(plan.assumed_grad_out) * float(plan.grad_multiplier)
     g_ptrs = cabi.ptr_array([g.data_ptr() if g is not None else None for g in grads])
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         stream = _stream_ptr(dev)
         ws, out, bwd_scale = ln.alloc_scalars(lib)
         w = ctypes.byref(plan.weights())
@@ -281,24 +322,30 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
 
 
 def _alloc_grads(students, needs: Sequence[bool], cls: bool):
-    grads = []
-    for s, need in zip(students, needs):
-        if not need:
-            grads.append(None)
-        elif cls:
-            grads.append(torch.zeros_like(s))  # only row 0 of each sample is written by the kernel
-        else:
-            grads.append(torch.empty_like(s))
+    """Gradient buffers for the layers that need them: ONE allocation carved into per-layer views (the
+    caching allocator and the Python overhead are paid once, not L times)."""
+    idx = [i for i, need in enumerate(needs) if need]
+    if not idx:
+        return [None] * len(students)
+    s0 = students[idx[0]]
+    make = torch.zeros if cls else torch.empty   # cls: only row 0 of each sample is written by the kernel
+    buf = make((len(idx),) + tuple(s0.shape), dtype=s0.dtype, device=s0.device)
+    views = buf.unbind(0)
+    grads = [None] * len(students)
+    for j, i in enumerate(idx):
+        grads[i] = views[j]
     return grads
 
 
 class _DistillFunction(torch.autograd.Function):
+    """Inputs: (plan, attention_mask, group, teachers tuple, *students).  The teachers ride in a plain tuple:
+    they never need gradients, so autograd does not have to look at them."""
+
     @staticmethod
-    def forward(ctx, plan: DistillPlan, attn_mask, group, n, *tensors):
-        students = _prepare(tensors[:n])
-        teachers = _prepare(tensors[n:])
-        needs = list(ctx.needs_input_grad[4:4 + n])
-        ctx.plan, ctx.n, ctx.needs, ctx.grads = plan, n, needs, None
+    def forward(ctx, plan: DistillPlan, attn_mask, group, teachers, *students):
+        students = _prepare(students)
+        needs = ctx.needs_input_grad[4:]
+        ctx.plan, ctx.needs, ctx.grads = plan, needs, None
         if plan.single_pass and any(needs):
             grads = _alloc_grads(students, needs, plan.cls)
             out, bwd_scale, ln = distill_fused(students, teachers, grads, attn_mask, plan, group)
@@ -312,16 +359,16 @@ class _DistillFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_total, _grad_aux):
-        ln, plan, n = ctx.launch, ctx.plan, ctx.n
-        none = (None,) * (4 + 2 * n)
+        ln, plan = ctx.launch, ctx.plan
         if grad_total is None or ln is None or not any(ctx.needs):
-            return none
+            return (None,) * (4 + len(ctx.needs))
         g = grad_total
         if g.dtype != torch.float32 or g.device != ln.device:
             g = g.to(device=ln.device, dtype=torch.float32)
         if plan.grad_multiplier != 1.0:
             g = g * plan.grad_multiplier
-        g = g.contiguous()
+        if not g.is_contiguous():
+            g = g.contiguous()
         if ctx.grads is not None:
             # one-pass step: gradients already exist; fix them up only if the upstream gradient differs
             grads, ctx.grads = ctx.grads, None
@@ -330,23 +377,32 @@ class _DistillFunction(torch.autograd.Function):
         else:
             grads = _alloc_grads(ln.students, ctx.needs, plan.cls)
             distill_backward(ln, grads, ctx.bwd_scale, g)
-        return (None, None, None, None, *grads, *([None] * n))
+        return (None, None, None, None, *grads)
 
 
 def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor], attn_mask, plan: DistillPlan,
-                 group=None):
+                 group=None, teachers_detached: bool = False):
     """Differentiable fused distillation loss over ``len(students)`` selected layers.
 
     Returns ``(total, aux)``: ``total`` is the 0-dim fp32 loss (gradients flow to ``students``),
     ``aux`` the non-differentiable ``[3L]`` vector of layer losses then (text, vision) losses.
     """
     students = list(students)
-    teachers = [t.detach() for t in teachers]
+    teachers = list(teachers) if teachers_detached else [t.detach() for t in teachers]
     if len(students) != len(teachers) or len(students) != len(plan.layers):
         raise ValueError("students / teachers / plan.layers length mismatch")
     dt = students[0].dtype
-    if any(t.dtype != dt for t in students) or any(t.dtype != dt for t in teachers):
+    for t in students:
+        if t.dtype != dt:
+            break
+    else:
+        for t in teachers:
+            if t.dtype != dt:
+                break
+        else:
+            dt = None
+    if dt is not None:
         # mixed dtypes: the reference up-casts both sides to fp32 under autocast (distillation.py:90,244)
         students = [s.float() for s in students]
         teachers = [t.float() for t in teachers]
-    return _DistillFunction.apply(plan, attn_mask, group, len(students), *students, *teachers)
+    return _DistillFunction.apply(plan, attn_mask, group, tuple(_prepare(teachers)), *students)

@@ -103,6 +103,11 @@ class FeatureDistillation(CLStrategy):
         self.assumed_grad_out = 1.0 / float(self.update_freq)
         # record only the distilled hidden states with forward hooks instead of output_hidden_states=True
         self.selective_capture = bool(kwargs.get("selective_capture", False))
+        # walk one memory-loader iterator instead of spawning a fresh one per replay step
+        self.persistent_memory_iterator = bool(kwargs.get("persistent_memory_iterator", False))
+        self._mem_iter = self._mem_iter_source = None
+        self._mem_epoch = 0
+        self._plan_cache = None
         self.last_layer_losses: Optional[torch.Tensor] = None   # device [3L]: layer, then (text, vision)
         self.last_layers: List[int] = []
         self._pending_log = None
@@ -136,7 +141,7 @@ class FeatureDistillation(CLStrategy):
     def replay(self, model):
         """Memory batch -> student forward (hidden states kept) -> replay LM loss + distillation loss.
         Returns ``(loss, n_examples)`` like ``distillation.py:84-103``."""
-        batch = next(iter(self.mem_dataloader))
+        batch = self._next_memory_batch()
         n_ex = batch["input_ids"].size(0)
         do_replay = self.replay_coeff > 0 and self.task_id > 0
         loss = None
@@ -156,18 +161,53 @@ class FeatureDistillation(CLStrategy):
             loss = dloss if loss is None else loss + dloss
         return loss, n_ex
 
+    def _next_memory_batch(self):
+        """The reference builds a NEW DataLoader iterator for every replay step
+        (``next(iter(self.mem_dataloader))``, ``distillation.py:85``), i.e. the first batch of a fresh
+        shuffle -- and a respawn of the loader's worker processes each time.  That stays the default;
+        ``persistent_memory_iterator=True`` walks one iterator and re-creates it only when an epoch over
+        the memory ends."""
+        if not self.persistent_memory_iterator:
+            return next(iter(self.mem_dataloader))
+        if self._mem_iter is None or self._mem_iter_source is not self.mem_dataloader:
+            self._mem_iter, self._mem_iter_source, self._mem_epoch = iter(self.mem_dataloader), self.mem_dataloader, 0
+        try:
+            return next(self._mem_iter)
+        except StopIteration:
+            self._mem_epoch += 1
+            sampler = getattr(self, "mem_sampler", None)
+            if hasattr(sampler, "set_epoch"):
+                sampler.set_epoch(self._mem_epoch)
+            self._mem_iter = iter(self.mem_dataloader)
+            return next(self._mem_iter)
+
     def distill(self, output, batch):
         """Sum over the selected layers of ``layer_coeff * distillation_coeff * layer_loss``
         (``distillation.py:105-122``) -- as one fused launch instead of a Python loop."""
         past_hidden_states = self._get_past_hidden_states(batch)
         layers = self.loss_weights.get_distillation_layers()
-        coeffs, modality_kind, lang_weights = self._tables(layers)
-        plan = self._plan(layers, coeffs, self.distillation_coeff, modality_kind, lang_weights)
-        total, aux = self._launch(plan, batch, [output.hidden_states[l] for l in layers],
-                                  [past_hidden_states[l] for l in layers])
+        plan = self._step_plan(layers)
+        hidden = output.hidden_states
+        total, aux = self._launch(plan, batch, [hidden[l] for l in layers], [past_hidden_states[l] for l in layers],
+                                  teachers_detached=True)
         self._record(aux, layers)
         self.step += 1
         return total
+
+    def _step_plan(self, layers) -> DistillPlan:
+        """The plan of the all-layer step, rebuilt only when something it depends on changes (the host
+        tables cost ~50 us of Python per step otherwise)."""
+        lw = self.loss_weights
+        coeff = getattr(lw, "lang_coeff", None)
+        key = (tuple(layers), self.distillation_coeff, self._cls_distillation, self._loss_kind, self.num_vision_tokens,
+               self.single_pass, self.assumed_grad_out, lw._modality_weighing_strategy, id(coeff),
+               getattr(coeff, "_version", None), id(lw.layer_coeffs))
+        if self._plan_cache is None or self._plan_cache[0] != key:
+            coeffs, modality_kind, lang_weights = self._tables(layers)
+            plan = self._plan(layers, coeffs, self.distillation_coeff, modality_kind, lang_weights)
+            plan.weights()
+            self._plan_cache = (key, plan)
+        return self._plan_cache[1]
 
     def feature_distillation(self, batch, hidden_states, past_hidden_states, layer: int):
         """Layer loss ``w_text * loss_text + w_vision * loss_vision`` of one layer, without the layer
@@ -196,13 +236,14 @@ class FeatureDistillation(CLStrategy):
                            cls=bool(self._cls_distillation), n_vis=self.num_vision_tokens,
                            single_pass=self.single_pass, assumed_grad_out=self.assumed_grad_out)
 
-    def _launch(self, plan: DistillPlan, batch, students, teachers):
+    def _launch(self, plan: DistillPlan, batch, students, teachers, teachers_detached=False):
         attn = None
         if not plan.cls:
             attn = batch["attention_mask"]
             if self.populate_batch_masks:
                 batch["lang_masks"], batch["image_masks"] = modality_masks(attn, self.num_vision_tokens)
-        return distill_loss(students, teachers, attn, plan, group=self.process_group)
+        return distill_loss(students, teachers, attn, plan, group=self.process_group,
+                            teachers_detached=teachers_detached)
 
     def _get_past_hidden_states(self, batch):
         with torch.no_grad():

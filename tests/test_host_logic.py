@@ -132,3 +132,44 @@ def test_constructed_exactly_like_train_py():
     fd.update_after_step(model=None, batch_idx=3)
     fd.update_after_new_task(model=None, dataset=None)
     fd.update_mask()
+
+
+class _ToyDataset(torch.utils.data.Dataset):
+    def __init__(self, n, base=0):
+        self.n, self.base = n, base
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return {"input_ids": torch.tensor([self.base + i])}
+
+
+def _collate(items):
+    return {"input_ids": torch.stack([it["input_ids"] for it in items])}
+
+
+def test_update_memory_and_model_like_reference():
+    """distillation.py:75-79,182-213: teacher snapshot, rng-sampled memory, loader rebuilt, task_id += 1."""
+    import numpy as np
+    fd = FeatureDistillation(8, Opts(), "vlpythia", distillation_modality_weighing_strategy="balanced",
+                             distillation_layer_weighing_strategy="equal", distillation_layer=None, num_hidden_layers=2)
+    fd.num_workers = 0
+    fd.data_hooks = (_collate, lambda loader: loader)           # stands in for mafed.data collate_fn / PrefetchLoader
+    model = torch.nn.Linear(2, 2)
+    model.train()
+    fd.update(dataset=_ToyDataset(50), model=model, dataloader=None)
+    assert fd.task_id == 1 and fd.past_model is not model and not fd.past_model.training
+    want = np.random.default_rng(Opts.seed).choice(np.arange(50), 4, replace=False)   # memory_per_task = 8 / 2
+    assert sorted(fd.datasets[0].indices) == sorted(want)
+    batch = fd._next_memory_batch()
+    assert set(batch["input_ids"].flatten().tolist()) <= set(int(i) for i in want)
+    assert isinstance(fd.mem_sampler, torch.utils.data.RandomSampler)
+    fd.update(dataset=_ToyDataset(30, base=1000), model=model, dataloader=None)
+    assert fd.task_id == 2 and len(fd.mem_dataloader.dataset) == 8
+    # persistent iterator: every memory sample exactly once per epoch, then a new epoch starts
+    fd.persistent_memory_iterator = True
+    seen = [fd._next_memory_batch()["input_ids"].flatten().tolist() for _ in range(2)]
+    assert sorted(sum(seen, [])) == sorted(x for ds in fd.datasets for x in
+                                           [int(ds.dataset[i]["input_ids"]) for i in ds.indices])
+    assert fd._next_memory_batch()["input_ids"].numel() == 4 and fd._mem_epoch == 1
