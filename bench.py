@@ -510,8 +510,10 @@ def run_e2e(args, fd, st, te, am, device, world, units_per_step):
     loss -> pinned host (D2H).  Layers are pipelined over three streams so copies overlap the kernels.
     """
     import torch.distributed as dist
-    from mafed_b200.host_step import HostStep
-    hs = HostStep(fd, st, te, am, device)
+    from mafed_b200.host_step import CHostStep, HostStep
+    # single GPU: the C ABI's own host-buffer entry (mafed_host_step_run); batch-sharded runs use the Python
+    # pipeline over the same kernels because it carries the cross-rank exchange
+    hs = (CHostStep if world == 1 else HostStep)(fd, st, te, am, device)
     for _ in range(2):
         hs.step()
     torch.cuda.synchronize()

@@ -179,6 +179,23 @@ int mafed_distill_token_norm_sums(const mafed_shape_t* shape, const void* const*
 int mafed_distill_modality_masks(const mafed_shape_t* shape, const int64_t* attn_mask, int64_t* lang_mask,
                                  int64_t* image_mask, void* stream);
 
+/* ---- host-buffer step: the whole path for callers whose hidden states live in HOST memory ----------
+ * create: allocates the device staging pool (mafed_host_step_device_bytes), three streams and events.
+ * run   : per layer H2D(student, teacher) -> one-pass fused kernel -> D2H(gradient), pipelined over the
+ *         three streams; returns when gradients (h_grad[l], student dtype) and h_out[1+3L] = {total, layer
+ *         losses, (text, vision) losses} are in host memory.  `grad_out` is the upstream gradient (host
+ *         value).  Host buffers should be pinned (mafed_host_register) for full PCIe bandwidth.
+ * Same results as mafed_distill_fused + mafed_distill_epilogue on device-resident tensors. */
+typedef struct mafed_host_step mafed_host_step_t;
+size_t mafed_host_step_device_bytes(const mafed_shape_t* shape);
+int mafed_host_step_create(const mafed_shape_t* shape, mafed_host_step_t** out);
+int mafed_host_step_run(mafed_host_step_t* step, const mafed_weights_t* weights, const void* const* h_student,
+                        const void* const* h_teacher, void* const* h_grad, const int64_t* h_mask, float grad_out,
+                        float* h_out);
+int mafed_host_step_destroy(mafed_host_step_t* step);
+int mafed_host_register(void* ptr, size_t bytes);
+int mafed_host_unregister(void* ptr);
+
 /* Experiment knobs (benchmarks only; process-global): kernel family for the next calls
  * (0 = default, 1 = ldg: register-staged 128-bit loads, 2 = tma: cp.async.bulk + mbarrier ring),
  * and integer tuning keys (see mafed_b200/cabi.py). */

@@ -31,6 +31,8 @@ EXPORTS = (
     "mafed_distill_bwd", "mafed_distill_fused", "mafed_distill_modality_masks", "mafed_distill_token_norm_sums",
     "mafed_distill_set_variant", "mafed_distill_set_tuning", "mafed_distill_scalar_stage_comm",
     "mafed_comm_handle_bytes", "mafed_comm_create", "mafed_comm_connect", "mafed_comm_status", "mafed_comm_destroy",
+    "mafed_host_step_device_bytes", "mafed_host_step_create", "mafed_host_step_run", "mafed_host_step_destroy",
+    "mafed_host_register", "mafed_host_unregister",
 )
 COMM_SUMS, COMM_COUNTS = 1, 2
 TUNE_NO_PDL = 15
@@ -111,6 +113,18 @@ def load():
         lib.mafed_comm_status.argtypes = [vp, ctypes.POINTER(i32)]
         lib.mafed_comm_destroy.restype = i32
         lib.mafed_comm_destroy.argtypes = [vp]
+        lib.mafed_host_step_device_bytes.restype = ctypes.c_size_t
+        lib.mafed_host_step_device_bytes.argtypes = [sh]
+        lib.mafed_host_step_create.restype = i32
+        lib.mafed_host_step_create.argtypes = [sh, ctypes.POINTER(vp)]
+        lib.mafed_host_step_run.restype = i32
+        lib.mafed_host_step_run.argtypes = [vp, wt, pp, pp, pp, vp, ctypes.c_float, vp]
+        lib.mafed_host_step_destroy.restype = i32
+        lib.mafed_host_step_destroy.argtypes = [vp]
+        lib.mafed_host_register.restype = i32
+        lib.mafed_host_register.argtypes = [vp, ctypes.c_size_t]
+        lib.mafed_host_unregister.restype = i32
+        lib.mafed_host_unregister.argtypes = [vp]
         lib.mafed_distill_token_norm_sums.restype = i32
         lib.mafed_distill_token_norm_sums.argtypes = [sh, pp, vp, vp, vp]
         lib.mafed_distill_modality_masks.restype = i32

@@ -7,6 +7,7 @@
 
 #include "distill_common.cuh"
 #include "distill_epilogue.cuh"
+#include "distill_host.cuh"
 #include "distill_ldg.cuh"
 #include "distill_tma.cuh"
 
@@ -553,6 +554,124 @@ int mafed_distill_modality_masks(const mafed_shape_t* shape, const int64_t* attn
              image_mask, n, (int)shape->T, (int)shape->n_vis);
   return (int)cudaPeekAtLastError();
 }
+
+// ---------------------------------------------------------------- host-buffer step
+size_t mafed_host_step_device_bytes(const mafed_shape_t* shape) {
+  if (check_shape(shape)) return 0;
+  const size_t layer = (size_t)shape->B * shape->T * shape->D * elem_size(shape->dtype);
+  const size_t mask = needs_mask(*shape) ? (size_t)shape->B * (shape->T - shape->n_vis) * sizeof(int64_t) : 0;
+  return 3 * layer * shape->n_layers + mask + (size_t)shape->n_layers * (mafed_distill_ws_bytes(1) + 64) + 4096;
+}
+
+int mafed_host_step_create(const mafed_shape_t* shape, mafed_host_step_t** out) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!out || shape->cls) return MAFED_E_ARG;
+  if (!device_info().ok) return MAFED_E_NODEVICE;
+  mafed_host_step* h = new mafed_host_step();
+  h->shape = *shape;
+  const int L = shape->n_layers;
+  h->layer_bytes = (((size_t)shape->B * shape->T * shape->D * elem_size(shape->dtype)) + 255) & ~(size_t)255;
+  h->mask_bytes = ((needs_mask(*shape) ? (size_t)shape->B * (shape->T - shape->n_vis) * sizeof(int64_t) : 0) + 255) & ~(size_t)255;
+  h->ws_bytes = (mafed_distill_ws_bytes(1) + 255) & ~(size_t)255;
+  const size_t total = 3 * h->layer_bytes * L + h->mask_bytes + (size_t)L * h->ws_bytes + (size_t)L * 6 * sizeof(float) + 1024;
+  cudaError_t e = cudaMalloc(&h->d_pool, total);
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_out, sizeof(float) * 4 * L);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    mafed_host_step_destroy(h);
+    return (int)e;
+  }
+  char* p = h->d_pool;
+  for (int l = 0; l < L; ++l) { h->d_s.push_back(p); p += h->layer_bytes; }
+  for (int l = 0; l < L; ++l) { h->d_t.push_back(p); p += h->layer_bytes; }
+  for (int l = 0; l < L; ++l) { h->d_g.push_back(p); p += h->layer_bytes; }
+  h->d_mask = reinterpret_cast<int64_t*>(p); p += h->mask_bytes;
+  h->d_ws = p; p += (size_t)L * h->ws_bytes;
+  h->d_out = reinterpret_cast<float*>(p); p += sizeof(float) * 4 * L;
+  h->d_scale = reinterpret_cast<float*>(p);
+  h->ev_in.resize(L);
+  h->ev_run.resize(L);
+  for (int l = 0; l < L; ++l) {
+    cudaEventCreateWithFlags(&h->ev_in[l], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_run[l], cudaEventDisableTiming);
+  }
+  *out = h;
+  return 0;
+}
+
+int mafed_host_step_run(mafed_host_step_t* h, const mafed_weights_t* weights, const void* const* h_student,
+                        const void* const* h_teacher, void* const* h_grad, const int64_t* h_mask, float grad_out,
+                        float* h_out) {
+  if (!h || !weights || !h_student || !h_teacher || !h_grad || !h_out) return MAFED_E_ARG;
+  const mafed_shape_t& sh = h->shape;
+  const int L = sh.n_layers;
+  if (needs_mask(sh) && !h_mask) return MAFED_E_ARG;
+  const size_t layer = (size_t)sh.B * sh.T * sh.D * elem_size(sh.dtype);
+  const size_t mask = needs_mask(sh) ? (size_t)sh.B * (sh.T - sh.n_vis) * sizeof(int64_t) : 0;
+  cudaError_t e = cudaSuccess;
+  if (mask) e = cudaMemcpyAsync(h->d_mask, h_mask, mask, cudaMemcpyHostToDevice, h->s_in);
+  for (int l = 0; l < L && e == cudaSuccess; ++l) {
+    e = cudaMemcpyAsync(h->d_s[l], h_student[l], layer, cudaMemcpyHostToDevice, h->s_in);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_t[l], h_teacher[l], layer, cudaMemcpyHostToDevice, h->s_in);
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[l], h->s_in);
+  }
+  if (e != cudaSuccess) return (int)e;
+  mafed_shape_t one = sh;
+  one.n_layers = 1;
+  for (int l = 0; l < L; ++l) {
+    mafed_weights_t w;
+    memset(&w, 0, sizeof(w));
+    w.modality_kind = weights->modality_kind;
+    w.distill_coeff = weights->distill_coeff;
+    w.layer_coeff[0] = weights->layer_coeff[l];
+    w.lang_weight[0] = weights->lang_weight[l];
+    cudaStreamWaitEvent(h->s_run, h->ev_in[l], 0);
+    const void* sp[1] = {h->d_s[l]};
+    const void* tp[1] = {h->d_t[l]};
+    void* gp[1] = {h->d_g[l]};
+    char* ws = h->d_ws + (size_t)l * h->ws_bytes;
+    int rc = mafed_distill_prologue(&one, &w, h->d_mask, nullptr, nullptr, h->d_scale + 2 * l, h->s_run);
+    if (!rc) rc = mafed_distill_fused(&one, sp, tp, gp, h->d_mask, h->d_scale + 2 * l, grad_out, ws, h->s_run);
+    if (!rc) rc = mafed_distill_epilogue(&one, &w, h->d_mask, ws, nullptr, h->d_out + 4 * l, nullptr, h->s_run);
+    if (rc) return rc;
+    cudaEventRecord(h->ev_run[l], h->s_run);
+    cudaStreamWaitEvent(h->s_out, h->ev_run[l], 0);
+    e = cudaMemcpyAsync(h_grad[l], h->d_g[l], layer, cudaMemcpyDeviceToHost, h->s_out);
+    if (e != cudaSuccess) return (int)e;
+  }
+  e = cudaMemcpyAsync(h->h_out, h->d_out, sizeof(float) * 4 * L, cudaMemcpyDeviceToHost, h->s_out);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_out);
+  if (e != cudaSuccess) return (int)e;
+  // out[1+3L] layout of the device path: total, layer losses, (text, vision) losses
+  double total = 0.0;
+  for (int l = 0; l < L; ++l) {
+    total += (double)h->h_out[4 * l];
+    h_out[1 + l] = h->h_out[4 * l + 1];
+    h_out[1 + L + 2 * l] = h->h_out[4 * l + 2];
+    h_out[1 + L + 2 * l + 1] = h->h_out[4 * l + 3];
+  }
+  h_out[0] = (float)total;
+  return 0;
+}
+
+int mafed_host_step_destroy(mafed_host_step_t* h) {
+  if (!h) return 0;
+  for (cudaEvent_t ev : h->ev_in) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : h->ev_run) cudaEventDestroy(ev);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_run) cudaStreamDestroy(h->s_run);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->d_pool) cudaFree(h->d_pool);
+  delete h;
+  return 0;
+}
+
+int mafed_host_register(void* ptr, size_t bytes) { return (int)cudaHostRegister(ptr, bytes, cudaHostRegisterDefault); }
+int mafed_host_unregister(void* ptr) { return (int)cudaHostUnregister(ptr); }
 
 int mafed_distill_set_variant(int variant) {
   if (variant < 0 || variant > 2) return MAFED_E_ARG;

@@ -86,3 +86,63 @@ class HostStep:
         cur.wait_stream(self.s_out)
         self.s_out.synchronize()                        # results are on the host when step() returns
         return self.h_loss
+
+
+class CHostStep:
+    """The same end-to-end step through the C ABI alone (``mafed_host_step_*``): host pointers in, host
+    pointers out, the copy / kernel pipeline runs inside the library on its own three streams.  torch is used
+    here only to own the pinned host buffers."""
+
+    def __init__(self, method, students, teachers, attention_mask, device, layers=None):
+        import ctypes
+
+        from mafed_b200 import cabi
+        from mafed_b200.distill_op import _DTYPES
+        self.lib = cabi.load()
+        self.device = torch.device(device)
+        self.layers = list(layers) if layers is not None else list(range(len(students)))
+        pin = dict(pin_memory=True)
+        self.h_s = [torch.empty(s.shape, dtype=s.dtype, **pin).copy_(s) for s in students]
+        self.h_t = [torch.empty(t.shape, dtype=t.dtype, **pin).copy_(t) for t in teachers]
+        self.h_mask = torch.empty(attention_mask.shape, dtype=torch.int64, **pin).copy_(attention_mask)
+        self.h_g = [torch.empty(s.shape, dtype=s.dtype, **pin) for s in students]
+        L = len(students)
+        self.h_out = torch.empty(1 + 3 * L, dtype=torch.float32, **pin)
+        B, T, D = students[0].shape
+        coeffs, kind, lang = method._tables(self.layers)
+        plan = method._plan(self.layers, coeffs, method.distillation_coeff, kind, lang)
+        self.weights = plan.weights()
+        self.shape = cabi.make_shape(L, B, T, method.num_vision_tokens, D, _DTYPES[students[0].dtype], plan.loss_kind)
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            cabi.check(self.lib.mafed_host_step_create(ctypes.byref(self.shape), ctypes.byref(self.handle)),
+                       "mafed_host_step_create")
+        self.s_ptrs = cabi.ptr_array([t.data_ptr() for t in self.h_s])
+        self.t_ptrs = cabi.ptr_array([t.data_ptr() for t in self.h_t])
+        self.g_ptrs = cabi.ptr_array([t.data_ptr() for t in self.h_g])
+        nbytes = lambda ts: sum(t.numel() * t.element_size() for t in ts)
+        self.h2d_bytes = nbytes(self.h_s) + nbytes(self.h_t) + nbytes([self.h_mask])
+        self.d2h_bytes = nbytes(self.h_g) + 4 * (1 + 3 * L)
+        self.note = "C ABI mafed_host_step_run: pinned host student/teacher/mask -> device, one-pass fused kernel " \
+                    "per layer, gradients + losses -> pinned host; 3-stream layer pipeline inside the library"
+
+    def step(self, grad_out: float = 1.0) -> torch.Tensor:
+        import ctypes
+
+        from mafed_b200 import cabi
+        with torch.cuda.device(self.device):
+            cabi.check(self.lib.mafed_host_step_run(self.handle, ctypes.byref(self.weights), self.s_ptrs, self.t_ptrs,
+                                                    self.g_ptrs, self.h_mask.data_ptr(), float(grad_out),
+                                                    self.h_out.data_ptr()), "mafed_host_step_run")
+        return self.h_out[0]
+
+    def close(self):
+        if self.handle:
+            self.lib.mafed_host_step_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     text = open(os.path.join(ROOT, "include", "mafed_distill.h")).read()
-    return sorted(set(re.findall(r"\b(mafed_(?:distill|comm)_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(mafed_(?:distill|comm|host)_[a-z_]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -113,3 +113,38 @@ def test_fullsize_properties_c4_shard():
     coeffs = [float(fd.loss_weights.get_layer_loss_weight(l)) for l in range(nh)]
     per_layer = fd.last_layer_losses[:nh].double().cpu()
     assert float((per_layer * torch.tensor(coeffs, dtype=torch.float64)).sum()) == pytest.approx(float(loss1), rel=1e-6)
+
+
+def test_offsets_beyond_2_gib_single_layer():
+    """C5's largest per-layer tensor (B=1024, T=512, D=2048, bf16 = 2.1 GiB): byte offsets need 64 bits."""
+    B, T, D = 1024, 512, 2048
+    free, _ = torch.cuda.mem_get_info()
+    if free < 12 * 2**30:
+        pytest.skip("needs 12 GiB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    s = torch.empty(B, T, D, device="cuda", dtype=torch.bfloat16)
+    t = torch.empty_like(s)
+    for i in range(0, B, 128):                                   # fill in slabs to bound temporaries
+        x = torch.randn(128, T, D, generator=g, device="cuda")
+        s[i:i + 128] = x.to(torch.bfloat16)
+        t[i:i + 128] = (x + 0.1 * torch.randn(128, T, D, generator=g, device="cuda")).to(torch.bfloat16)
+    del x
+    am = torch.ones(B, T - 256, dtype=torch.int64, device="cuda")
+    am[::3, :100] = 0
+    meta = dict(modality="equal", layer_strategy="single", loss="mse", gamma=0.5, layer=0, n_vis=256, num_hidden_layers=1)
+    for variant in (cabi.VARIANT_TMA, cabi.VARIANT_LDG):
+        loss, grads, _ = _run(meta, [s], [t], am, variant=variant)
+        # reference in slabs (fp64 accumulation of fp32 row sums)
+        w = torch.cat([torch.ones(B, 256, device="cuda"), am.float()], 1)
+        tot = torch.zeros((), dtype=torch.float64, device="cuda")
+        for i in range(0, B, 128):
+            d = s[i:i + 128].float() - t[i:i + 128].float()
+            tot += (d.pow(2).sum(-1).double() * w[i:i + 128]).sum()
+        want = float(tot / (D * w.sum().double()))               # "equal" weighting == mean over valid tokens
+        assert float(loss) == pytest.approx(want, rel=1e-5)
+        gscale = 2.0 / (D * float(w.sum()))
+        for i in (0, 384, 896):                                  # spot-check slabs at the start, middle and end
+            d = (s[i:i + 128].float() - t[i:i + 128].float()) * (gscale * w[i:i + 128]).unsqueeze(-1)
+            assert rel_err(grads[0][i:i + 128].float(), d) < 2e-3
+        assert float(grads[0][0, 256:356].abs().max()) == 0.0    # padded rows of sample 0
+        del grads
