@@ -199,6 +199,40 @@ def cpu_baseline(wl, sample_B=None, iters=3, warmup=1):
             "ms_per_sample_step": 1e3 * min(times)}
 
 
+def eager_gpu_baseline(wl, st, te, am, iters=5, warmup=2):
+    """The reference's own op chain (oracle port: ATen kernels + autograd, distillation.py:105-166 under
+    autocast) run on the SAME GPU on the same tensors -- what the unmodified reference would spend on this
+    path on a B200.  A baseline leg like `cpu_baseline`; the product never calls it."""
+    from oracle import distill_oracle as O
+    _, n_tuple, n_sel, B, txt, D, dt = WORKLOADS[wl]
+    cfg = O.OracleConfig(modality_strategy=RECIPE["modality"], layer_strategy=RECIPE["layer_strategy"],
+                         gamma=RECIPE["gamma"], num_hidden_layers=n_sel, distillation_layer=None, loss=RECIPE["loss"],
+                         num_vision_tokens=N_VIS)
+    leaves = [s.detach().requires_grad_(True) for s in st]
+
+    def step():
+        for s in leaves:
+            s.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            total, per_layer, _ = O.distill(leaves, te, am, cfg)
+            _ = [float(v) for v in per_layer.values()]      # the reference's per-layer .item() for W&B (:165)
+        total.backward()
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    units = B * (N_VIS + txt) * n_sel
+    return {"value": units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "what": "reference op chain (oracle port, eager PyTorch ATen kernels + autograd, autocast bf16) on this GPU"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -450,6 +484,11 @@ def main():
             line["e2e"] = run_e2e(args, fd, st, te, am, device, world, units_per_step)
         except Exception as exc:  # keep the headline line even if the host path cannot allocate
             line["e2e"] = {"error": repr(exc)}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["eager_torch_gpu"] = eager_gpu_baseline(wl, st, te, am)
+        except Exception as exc:
+            line["eager_torch_gpu"] = {"error": repr(exc)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
             base = cpu_baseline(wl)

@@ -1,57 +1,49 @@
-"""Continual-learning strategy interface -- mirror of ``mafed/methods/base.py:1-57``.
+"""Strategy interface the trainer drives (mirror of the reference's ``mafed/methods/base.py``).
 
-Same attribute names and hook signatures as the reference so that ``mafed/train.py`` and
-``mafed/model/vqa_cont_learner.py`` drive either implementation unchanged.
+Only the contract is shared with the reference: attribute names (``task_id``, ``reg_lambda``, ``mask``,
+``scaler``, ``update_freq``) and hook names / signatures, because ``mafed/train.py:181-213`` and
+``mafed/model/vqa_cont_learner.py:211-254`` call them by name.
 """
+from __future__ import annotations
+
+
+def _accumulation_window(options) -> int:
+    """``opts.accumulate_grad_batches`` when present and truthy, else 1 (reference ``base.py:12-15``)."""
+    window = getattr(options, "accumulate_grad_batches", None) if options else None
+    return window if window else 1
 
 
 class CLStrategy:
-    """Base class of the continual-learning strategies (``mafed/methods/base.py:1-47``).
-
-    Attributes read by the callers: ``task_id``, ``reg_lambda``, ``mask``, ``scaler``,
-    ``update_freq`` (= ``opts.accumulate_grad_batches`` when truthy, else 1).
-    """
+    """A continual-learning method as seen by the training loop."""
 
     def __init__(self, reg_lambda=1.0, mask=None, scaler=None, **kwargs):
-        opts = kwargs.get("opts")
-        accumulate = getattr(opts, "accumulate_grad_batches", None) if opts else None
-        self.update_freq = accumulate if (opts and accumulate) else 1
-        self.scaler = scaler
-        self.mask = mask
-        self.reg_lambda = reg_lambda
-        self.task_id = 0
+        self.task_id, self.reg_lambda, self.mask, self.scaler = 0, reg_lambda, mask, scaler
+        self.update_freq = _accumulation_window(kwargs.get("opts"))
 
-    # ---- hooks called by the trainer (train.py:181-213, vqa_cont_learner.py:211-254)
+    def _hook(self, **kwargs):
+        return None
+
+    # between tasks / after model init / after backward / after an optimizer step: no-ops unless overridden
+    update_after_new_task = _hook
+    update_after_backward = _hook
+    update_after_step = _hook
+
     def update(self, model, **kwargs):
-        """Between tasks."""
         self.task_id += 1
 
-    def update_after_new_task(self, **kwargs):
-        """After the model for the new task is initialised; nothing to do by default."""
-
-    def update_after_backward(self, **kwargs):
-        """After ``loss.backward()``; nothing to do by default."""
-
-    def update_after_step(self, **kwargs):
-        """After an optimizer step; nothing to do by default."""
-
     def compute_loss(self, model, loss, **kwargs):
-        raise NotImplementedError
+        raise NotImplementedError(f"{type(self).__name__} does not define a task loss")
 
     def replay(self, model, **kwargs):
-        """Default: no memory, hence no replay loss and zero examples."""
-        return None, 0
+        return None, 0          # (replay loss, number of memory examples)
 
     def _is_batch_after_step(self, batch_idx=0):
-        """True on the micro-batch that closes a gradient-accumulation window."""
-        return (batch_idx + 1) % self.update_freq == 0
+        """Does this micro-batch close a gradient-accumulation window?"""
+        return not (batch_idx + 1) % self.update_freq
 
 
 class Naive(CLStrategy):
-    """Plain fine-tuning: the task loss is returned untouched (``base.py:50-57``)."""
-
-    def __init__(self, **kwargs):
-        super().__init__(**kwargs)
+    """Sequential fine-tuning: nothing is added to the task loss."""
 
     def compute_loss(self, model, loss, **kwargs):
         return loss

@@ -85,9 +85,10 @@ def layer_plan(cfg: OracleConfig) -> Tuple[List[int], Optional[torch.Tensor], st
 def build_masks(attention_mask: torch.Tensor, n_vis: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """distillation.py:134-144."""
     bsz, txt = attention_mask.shape
-    lang = torch.zeros((bsz, txt + n_vis), dtype=attention_mask.dtype)
+    dev = attention_mask.device  # the reference allocates on the CPU and copies with .to(device)
+    lang = torch.zeros((bsz, txt + n_vis), dtype=attention_mask.dtype).to(dev)
     lang[:, n_vis:] = attention_mask
-    img = torch.zeros((bsz, txt + n_vis), dtype=attention_mask.dtype)
+    img = torch.zeros((bsz, txt + n_vis), dtype=attention_mask.dtype).to(dev)
     img[:, :n_vis] = 1
     return lang, img
 
@@ -183,7 +184,7 @@ def forward_backward(students, teachers, attention_mask, cfg: OracleConfig, grad
     teachers = [t.detach() for t in teachers]
     if autocast_bf16 is None:
         autocast_bf16 = students[0].dtype != torch.float32
-    ctx = torch.autocast("cpu", dtype=torch.bfloat16) if autocast_bf16 else contextlib.nullcontext()
+    ctx = torch.autocast(students[0].device.type, dtype=torch.bfloat16) if autocast_bf16 else contextlib.nullcontext()
     with ctx:
         total, per_layer, per_mod = distill(students, teachers, attention_mask, cfg)
     (total * grad_out).backward()
