@@ -397,6 +397,8 @@ def main():
             sync_all()
         return e0.elapsed_time(e1), sampler, loss
 
+    step_stats = {}
+
     def stage_loop(step_fn):
         for _ in range(args.warmup):
             step_fn()
@@ -407,6 +409,8 @@ def main():
         sync_all()
         a = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
         b = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+        per_step = [e[0].elapsed_time(e[2]) for e in evs]
+        step_stats[step_fn.__name__] = {"median_ms": statistics.median(per_step), "best_ms": min(per_step)}
         return a, b, evs[0][0].elapsed_time(evs[-1][2])
 
     fwd_ms, bwd_ms, two_raw_ms = stage_loop(two_pass_step)
@@ -450,6 +454,7 @@ def main():
                           "frac_of_nominal_8000": gbs(fused_bytes, ms_per_step) / 8000.0, "bytes_per_unit": 3 * row_bytes},
         "kernel_value": units_per_step / (one_raw_ms / args.steps * 1e-3),
         "host_us_per_step": host_us.get(True),
+        "kernel_level_step_ms": {"one_pass": step_stats.get("one_pass_step"), "two_pass": step_stats.get("two_pass_step")},
         "two_pass": {
             "note": "north_star's two-kernel form (fused forward, then fused backward): 5*D*e bytes per token*layer",
             "value": units_per_step / (two_ms * 1e-3), "ms_per_step": two_ms,
@@ -466,7 +471,9 @@ def main():
         },
         # one-pass step: prologue, fused kernel, epilogue, backward fix-up; the NVLink peer exchange rides inside
         # the two scalar stages, the NCCL fallback adds a counts kernel and a reduce kernel
-        "gpu_launches": args.steps * (4 if (world == 1 or peer_path) else 6),
+        # per step: modality masks, fused kernel (scale table derived in-kernel), epilogue, backward fix-up;
+        # batch-sharded: + a prologue carrying the counts exchange (peer path) or counts/reduce kernels (NCCL)
+        "gpu_launches": args.steps * (4 if world == 1 else (5 if peer_path else 7)),
         "exchange": "none" if world == 1 else ("nvlink peer-memory mailboxes inside the scalar-stage kernels"
                                                if peer_path else "nccl allreduce"),
         "loss": float(loss.detach()),

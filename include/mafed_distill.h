@@ -140,10 +140,15 @@ int mafed_distill_bwd(const mafed_shape_t* shape, const void* const* student_ptr
  * scale depends only on the token counts and the host weight tables (not on the loss), so it is
  * known before the pass; the upstream gradient is assumed to be `assumed_grad_out` (1/accumulate_
  * grad_batches under Lightning, vqa_cont_learner.py:213-236) and checked later by
- * mafed_distill_bwd(..., skip_if_equals).  A NULL entry in grad_ptrs still contributes to the sums. */
+ * mafed_distill_bwd(..., skip_if_equals).  A NULL entry in grad_ptrs still contributes to the sums.
+ * `weights` != NULL (single-rank step): the call also produces `bwd_scale` -- for masks of <= 16 Ki
+ * entries every CTA of the kernel derives the table itself while its first tiles are in flight (no
+ * prologue launch), otherwise a prologue is launched first.  `weights` == NULL: `bwd_scale` is an input
+ * (mafed_distill_prologue with the allreduced counts, batch-sharded step). */
 int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_ptrs,
                         const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
-                        const float* bwd_scale, float assumed_grad_out, void* ws, void* stream);
+                        const mafed_weights_t* weights, float* bwd_scale, float assumed_grad_out, void* ws,
+                        void* stream);
 
 /* ---- batch-sharded step without NCCL on the critical path: peer-memory communicator ----------------
  * One process per GPU of one NVLink/NVSwitch box.  Each rank creates a small mailbox (cudaMalloc +

@@ -101,7 +101,7 @@ def load():
         lib.mafed_distill_bwd.restype = i32
         lib.mafed_distill_bwd.argtypes = [sh, pp, pp, pp, vp, vp, vp, ctypes.POINTER(ctypes.c_float), vp]
         lib.mafed_distill_fused.restype = i32
-        lib.mafed_distill_fused.argtypes = [sh, pp, pp, pp, vp, vp, ctypes.c_float, vp, vp]
+        lib.mafed_distill_fused.argtypes = [sh, pp, pp, pp, vp, wt, vp, ctypes.c_float, vp, vp]
         lib.mafed_distill_scalar_stage_comm.restype = i32
         lib.mafed_distill_scalar_stage_comm.argtypes = [sh, wt, i32, vp, vp, vp, vp, vp, vp, i32, vp]
         lib.mafed_comm_handle_bytes.restype = i32

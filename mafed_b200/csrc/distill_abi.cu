@@ -17,11 +17,12 @@ namespace {
 enum Pass { kPassFwd = 0, kPassBwd = 1, kPassFused = 2 };
 
 std::atomic<int> g_variant{0};   // 0 default, 1 ldg, 2 tma
-std::atomic<int> g_tune[16] = {};  // experiment knobs, see mafed_distill_set_tuning
+std::atomic<int> g_tune[24] = {};  // experiment knobs, see mafed_distill_set_tuning
 
 // per-pass keys: base + pass (fwd, bwd, fused)
 enum TuneKey { kTuneTmaStages = 0, kTuneTmaRows = 3, kTuneVariant = 6, kTuneTmaWarps = 9, kTuneLdgBlocksPerSm = 10,
-               kTuneBwdForward = 11, kTuneGridMul = 12, kTuneLoadPolicy = 13, kTuneStorePolicy = 14, kTuneNoPdl = 15 };
+               kTuneBwdForward = 11, kTuneGridMul = 12, kTuneLoadPolicy = 13, kTuneStorePolicy = 14, kTuneNoPdl = 15,
+               kTuneNoInlineScale = 16 };
 
 // Launch with programmatic dependent launch enabled: the kernel may start its prologue while its
 // predecessor in the stream is finishing; all kernels here call griddepcontrol.wait before touching
@@ -268,6 +269,22 @@ int dispatch(const mafed_shape_t& sh, PathParams& p, int pass, cudaStream_t st, 
     case MAFED_BF16: return dispatch_loss<__nv_bfloat16>(p, loss, vector_ok, pass, st);
     default: return dispatch_loss<__half>(p, loss, vector_ok, pass, st);
   }
+}
+
+// Will `dispatch` take the TMA-ring kernels for this call?  (Same decision, made ahead of the launch.)
+bool uses_tma(const mafed_shape_t& sh, const PathParams& p, int pass) {
+  const size_t es = elem_size(sh.dtype);
+  bool vector_ok = ((size_t)sh.D * es) % 16 == 0 && ((size_t)p.row_stride * es) % 16 == 0;
+  for (int l = 0; l < sh.n_layers && vector_ok; ++l)
+    vector_ok = aligned_to(p.s[l], 16) && aligned_to(p.t[l], 16) && (pass == kPassFwd || aligned_to(p.g[l], 16));
+  if (!vector_ok) return false;
+  int variant = g_tune[kTuneVariant + pass].load();
+  if (variant == 0) variant = g_variant.load();
+  if (variant != 0 && variant != 2) return false;
+  PathParams q = p;
+  q.n_chunks = (int)((size_t)sh.D * es / 16);
+  TmaGeom geo;
+  return tma_geometry(q, pass, geo);
 }
 
 // Common argument checks + pointer-table copy for the three streaming passes.
@@ -531,8 +548,8 @@ int mafed_distill_bwd(const mafed_shape_t* shape, const void* const* student_ptr
 }
 
 int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
-                        void* const* grad_ptrs, const int64_t* attn_mask, const float* bwd_scale, float assumed_grad_out,
-                        void* ws, void* stream) {
+                        void* const* grad_ptrs, const int64_t* attn_mask, const mafed_weights_t* weights, float* bwd_scale,
+                        float assumed_grad_out, void* ws, void* stream) {
   if (!grad_ptrs || !bwd_scale || !ws) return MAFED_E_ARG;
   PathParams p;
   int rc = fill_params(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, p);
@@ -540,6 +557,23 @@ int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_p
   p.bwd_scale = bwd_scale;
   p.fixed_gout = assumed_grad_out;
   p.ws = reinterpret_cast<float*>(ws);
+  if (weights != nullptr) {
+    // single-rank step: the scale table is this call's business.  Small masks: every CTA of the TMA kernel
+    // derives it itself while its first tiles are in flight; otherwise one prologue launch.
+    const long long n_mask = needs_mask(*shape) ? (long long)shape->B * (shape->T - shape->n_vis) : 0;
+    if (n_mask <= 16384 && !g_tune[kTuneNoInlineScale].load() && uses_tma(*shape, p, kPassFused)) {
+      p.inline_scale = 1;
+      p.loss_kind = shape->loss_kind;
+      p.n_mask = n_mask;
+      p.n_vis_rows = shape->cls ? (double)shape->B : (double)shape->B * (double)shape->n_vis;
+      p.bwd_scale_out = bwd_scale;
+      p.w = *weights;
+    } else {
+      rc = launch_scalar_stage(*shape, weights, MAFED_STAGE_COUNTS | MAFED_STAGE_SCALE, attn_mask, nullptr, nullptr,
+                               nullptr, bwd_scale, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+  }
   return dispatch(*shape, p, kPassFused, (cudaStream_t)stream);
 }
 
@@ -633,8 +667,7 @@ int mafed_host_step_run(mafed_host_step_t* h, const mafed_weights_t* weights, co
     const void* tp[1] = {h->d_t[l]};
     void* gp[1] = {h->d_g[l]};
     char* ws = h->d_ws + (size_t)l * h->ws_bytes;
-    int rc = mafed_distill_prologue(&one, &w, h->d_mask, nullptr, nullptr, h->d_scale + 2 * l, h->s_run);
-    if (!rc) rc = mafed_distill_fused(&one, sp, tp, gp, h->d_mask, h->d_scale + 2 * l, grad_out, ws, h->s_run);
+    int rc = mafed_distill_fused(&one, sp, tp, gp, h->d_mask, &w, h->d_scale + 2 * l, grad_out, ws, h->s_run);
     if (!rc) rc = mafed_distill_epilogue(&one, &w, h->d_mask, ws, nullptr, h->d_out + 4 * l, nullptr, h->s_run);
     if (rc) return rc;
     cudaEventRecord(h->ev_run[l], h->s_run);
@@ -680,7 +713,7 @@ int mafed_distill_set_variant(int variant) {
 }
 
 int mafed_distill_set_tuning(int key, int value) {
-  if (key < 0 || key >= 16) return MAFED_E_ARG;
+  if (key < 0 || key >= 24) return MAFED_E_ARG;
   g_tune[key].store(value);
   return 0;
 }

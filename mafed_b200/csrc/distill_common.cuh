@@ -38,6 +38,13 @@ struct PathParams {
   float fixed_gout;              // fused pass: upstream gradient assumed at forward time (host value)
   int skip_if_gout_equals;       // backward fix-up: return at once when *grad_out == fixed_gout
   int single_input;              // 1: only `s` is read (token-norm sums); the teacher table is ignored
+  // one-pass step with the prologue folded in: every CTA derives the scale table from the mask itself
+  int inline_scale;              // 1: compute counts + scale in the kernel (weights below), else read bwd_scale
+  int loss_kind;
+  long long n_mask;              // B * txt
+  double n_vis_rows;             // B * n_vis
+  float* bwd_scale_out;          // CTA 0 publishes the table for the later backward fix-up
+  mafed_weights_t w;
   int load_policy;               // L2 eviction hint for student/teacher reads (CachePolicy)
   int store_policy;              // L2 eviction hint for gradient writes
 };
@@ -176,6 +183,35 @@ __device__ __forceinline__ float row_weight(const PathParams& p, long long row, 
   if (t < p.n_vis) { modality = 1; return 1.f; }
   modality = 0;
   return (float)__ldg(p.mask + b * p.txt + (t - p.n_vis));
+}
+
+// Modality weights of layer l (distillation_loss_weights.py:71-79,148-174) as (w_text, w_vision).
+__device__ __forceinline__ void modality_weights(const mafed_weights_t& w, int l, double n_text, double n_vis,
+                                                 double& wt, double& wv) {
+  if (w.modality_kind == MAFED_MODW_EQUAL) {
+    wt = (double)(float)(n_text / (n_text + n_vis));
+    wv = (double)(float)(n_vis / (n_text + n_vis));
+  } else if (w.modality_kind == MAFED_MODW_TABLE) {
+    wt = (double)w.lang_weight[l];
+    wv = (double)(float)(1.0 - wt);
+  } else if (w.modality_kind == MAFED_MODW_TEXT_ONLY) {
+    wt = 1.0;
+    wv = 0.0;
+  } else {  // CLS: vision slot only
+    wt = 0.0;
+    wv = 1.0;
+  }
+}
+
+// Backward scale of layer l: c_l * coeff * w_m * k / n_m with k = 2/D (mse) or 1 (cosine).
+__device__ __forceinline__ void backward_scales(const mafed_weights_t& w, int l, double n_text, double n_vis,
+                                                int loss_kind, int D, float& s_text, float& s_vis) {
+  double wt, wv;
+  modality_weights(w, l, n_text, n_vis, wt, wv);
+  const double c = (double)w.layer_coeff[l] * (double)w.distill_coeff;
+  const double g = (loss_kind == MAFED_LOSS_MSE) ? 2.0 / (double)D : 1.0;
+  s_text = (w.modality_kind == MAFED_MODW_CLS) ? 0.f : (float)(c * wt * g / n_text);
+  s_vis = (w.modality_kind == MAFED_MODW_TEXT_ONLY) ? 0.f : (float)(c * wv * g / n_vis);
 }
 
 // Per-element math.  mse: sum (h-p)^2.  cosine: dot, |h|^2, |p|^2.

@@ -127,11 +127,8 @@ __global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant_
       p.out[1 + L + 2 * l] = (float)text_loss;
       p.out[1 + L + 2 * l + 1] = (float)vis_loss;
     }
-    if (want_scale) {
-      const double g = (p.loss_kind == MAFED_LOSS_MSE) ? 2.0 * k : 1.0;
-      p.bwd_scale[2 * l] = cls ? 0.f : (float)(c * wt * g / n_text);
-      p.bwd_scale[2 * l + 1] = text_only ? 0.f : (float)(c * wv * g / n_vis);
-    }
+    if (want_scale)
+      backward_scales(p.w, l, n_text, n_vis, p.loss_kind, p.D, p.bwd_scale[2 * l], p.bwd_scale[2 * l + 1]);
   }
   if (!want_loss) return;
   __syncthreads();

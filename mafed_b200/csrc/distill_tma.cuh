@@ -263,6 +263,36 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
     tma_producer<T>(p, geo, dyn_smem, sm.full, sm.empty, sm.meta, lane, !FUSED);
     return;
   }
+  // Scale table in shared memory.  One-pass step with the prologue folded in: while the producer's first
+  // tiles are in flight, the consumer warps count the valid text tokens themselves (the mask is a few KB,
+  // L2-resident) and derive the table; CTA 0 publishes it for the later backward fix-up.
+  __shared__ float s_scale[2 * kMaxLayers];
+  if (FUSED && p.inline_scale) {
+    __shared__ long long s_cnt[NCW];
+    long long c = 0;
+    for (long long i = threadIdx.x; i < p.n_mask; i += NCW * 32) c += p.mask[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_cnt[warp] = c;
+    named_bar_sync(1, NCW * 32);
+    if ((int)threadIdx.x < p.n_layers) {
+      long long n_text = 0;
+#pragma unroll
+      for (int i = 0; i < NCW; ++i) n_text += s_cnt[i];
+      float st, sv;
+      backward_scales(p.w, threadIdx.x, (double)n_text, p.n_vis_rows, p.loss_kind, p.D, st, sv);
+      s_scale[2 * threadIdx.x] = st;
+      s_scale[2 * threadIdx.x + 1] = sv;
+      if (blockIdx.x == 0) {
+        p.bwd_scale_out[2 * threadIdx.x] = st;
+        p.bwd_scale_out[2 * threadIdx.x + 1] = sv;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < 2 * p.n_layers; i += NCW * 32) s_scale[i] = __ldg(p.bwd_scale + i);
+  }
+  named_bar_sync(1, NCW * 32);
+
   const long long tiles_per_layer = (p.n_rows + geo.rows - 1) / geo.rows;
   const long long total = tiles_per_layer * p.n_layers;
   const uint32_t row_bytes = (uint32_t)p.n_chunks * 16u;
@@ -288,7 +318,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
     if (FUSED || gb != nullptr) {
       for (int r = first; r < mt.n_rows; r += NCW) {
         char* grow = gb + (mt.row0 + r) * row_pitch;
-        const float w = mt.w[r] * (gout * __ldg(p.bwd_scale + 2 * l + mt.mod[r]));
+        const float w = mt.w[r] * (gout * s_scale[2 * l + mt.mod[r]]);
         if (mt.w[r] == 0.f) {  // padded text row: nothing was fetched; grad = 0 * scale (zero, or NaN if scale is)
           float o[NE];
 #pragma unroll

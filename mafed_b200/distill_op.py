@@ -290,7 +290,7 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
             cabi.check(lib.mafed_distill_scalar_stage_comm(
                 ln.shape_ref, w, cabi.STAGE_COUNTS | cabi.STAGE_SCALE, ln.mask_ptr, None, sums.data_ptr(), None,
                 bwd_scale.data_ptr(), peer.handle, cabi.COMM_COUNTS, stream), "prologue_comm")
-            cabi.check(lib.mafed_distill_fused(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr,
+            cabi.check(lib.mafed_distill_fused(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr, None,
                                                bwd_scale.data_ptr(), fixed, ws.data_ptr(), stream),
                        "mafed_distill_fused")
             cabi.check(lib.mafed_distill_scalar_stage_comm(
@@ -304,11 +304,10 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
             allreduce_sums(sums[2 * L:], pg)
             cabi.check(lib.mafed_distill_prologue(ln.shape_ref, w, None, sums.data_ptr(), None, bwd_scale.data_ptr(),
                                                   stream), "mafed_distill_prologue")
-        else:
-            cabi.check(lib.mafed_distill_prologue(ln.shape_ref, w, ln.mask_ptr, None, None, bwd_scale.data_ptr(),
-                                                  stream), "mafed_distill_prologue")
+        # single rank: passing the weights makes the kernel derive the scale table itself (no prologue launch)
         cabi.check(lib.mafed_distill_fused(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr,
-                                           bwd_scale.data_ptr(), fixed, ws.data_ptr(), stream), "mafed_distill_fused")
+                                           None if distributed else w, bwd_scale.data_ptr(), fixed, ws.data_ptr(),
+                                           stream), "mafed_distill_fused")
         if distributed:
             cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_REDUCE, None, ws.data_ptr(),
                                                       sums.data_ptr(), None, None, stream), "reduce")

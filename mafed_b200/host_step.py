@@ -4,8 +4,8 @@ This is the end-to-end form of the path for callers whose hidden states are not 
 device: every step copies student / teacher / mask host -> device, runs the fused forward,
 epilogue and backward, and copies the gradients and the loss device -> host.  Layers are
 pipelined over three streams (copy-in, compute, copy-out) so that PCIe transfers in both directions
-overlap each other and the kernels; per layer the work is three C-ABI launches
-(``mafed_distill_prologue`` / ``_fused`` / ``_epilogue`` with ``n_layers = 1``).
+overlap each other and the kernels; per layer the work is two C-ABI calls
+(``mafed_distill_fused`` + ``mafed_distill_epilogue`` with ``n_layers = 1``).
 
 The backward of a layer needs only the token counts and the host weight tables, not the other
 layers' sums, which is what makes the per-layer pipeline legal.
