@@ -469,8 +469,6 @@ def main():
                               "frac_of_nominal_8000": gbs(fwd_bytes + bwd_bytes, two_ms) / 8000.0,
                               "bytes_per_unit": 5 * row_bytes},
         },
-        # one-pass step: prologue, fused kernel, epilogue, backward fix-up; the NVLink peer exchange rides inside
-        # the two scalar stages, the NCCL fallback adds a counts kernel and a reduce kernel
         # per step: modality masks, fused kernel (scale table derived in-kernel), epilogue, backward fix-up;
         # batch-sharded: + a prologue carrying the counts exchange (peer path) or counts/reduce kernels (NCCL)
         "gpu_launches": args.steps * (4 if world == 1 else (5 if peer_path else 7)),
@@ -509,7 +507,7 @@ def main():
         dist.destroy_process_group()
 
 
-def other_workloads(skip, device, peak, steps=40, warmup=5):
+def other_workloads(skip, device, peak, steps=100, warmup=20):
     """The other BASELINE.json configurations that fit one GPU, through the public API (one-pass step):
     tokens*layers/s and the step's algorithmic GB/s.  Informational; the headline stays `value`."""
     out = {}
@@ -545,7 +543,6 @@ def other_workloads(skip, device, peak, steps=40, warmup=5):
                    "frac": gbs / peak, "bytes_per_unit": 3 * D * esize,
                    "note": "L2-assisted: student+teacher+gradient = 234 MB vs 126 MB L2" if wl == "C1" else ""}
         del st, te, leaves, fd
-        torch.cuda.empty_cache()
     return out
 
 
