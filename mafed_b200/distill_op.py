@@ -404,4 +404,22 @@ def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tens
         # mixed dtypes: the reference up-casts both sides to fp32 under autocast (distillation.py:90,244)
         students = [s.float() for s in students]
         teachers = [t.float() for t in teachers]
-    return _DistillFunction.apply(plan, attn_mask, group, tuple(_prepare(teachers)), *students)
+    teachers = _prepare(teachers)
+    n = len(students)
+    if n <= cabi.MAX_LAYERS:
+        return _DistillFunction.apply(plan, attn_mask, group, tuple(teachers), *students)
+    # more selected layers than one launch carries (MAFED_MAX_LAYERS): chunk and add the partial totals
+    total, layer_losses, modal_losses = None, [], []
+    for lo in range(0, n, cabi.MAX_LAYERS):
+        hi = min(n, lo + cabi.MAX_LAYERS)
+        sub = DistillPlan(layers=plan.layers[lo:hi], layer_coeffs=plan.layer_coeffs[lo:hi],
+                          distill_coeff=plan.distill_coeff, modality_kind=plan.modality_kind,
+                          lang_weights=None if plan.lang_weights is None else plan.lang_weights[lo:hi],
+                          loss_kind=plan.loss_kind, cls=plan.cls, n_vis=plan.n_vis,
+                          grad_multiplier=plan.grad_multiplier, single_pass=plan.single_pass,
+                          assumed_grad_out=plan.assumed_grad_out)
+        part, aux = _DistillFunction.apply(sub, attn_mask, group, tuple(teachers[lo:hi]), *students[lo:hi])
+        total = part if total is None else total + part
+        layer_losses.append(aux[: hi - lo])
+        modal_losses.append(aux[hi - lo:])
+    return total, torch.cat(layer_losses + modal_losses)

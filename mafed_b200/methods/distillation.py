@@ -205,7 +205,8 @@ class FeatureDistillation(CLStrategy):
         if self._plan_cache is None or self._plan_cache[0] != key:
             coeffs, modality_kind, lang_weights = self._tables(layers)
             plan = self._plan(layers, coeffs, self.distillation_coeff, modality_kind, lang_weights)
-            plan.weights()
+            if len(layers) <= cabi.MAX_LAYERS:
+                plan.weights()
             self._plan_cache = (key, plan)
         return self._plan_cache[1]
 

@@ -277,3 +277,15 @@ def test_modality_masks_kernel_matches_reference_construction():
     assert torch.equal(a.cpu(), lang) and torch.equal(b.cpu(), img)
     a32, _ = modality_masks(am.int(), 4)
     assert a32.dtype == torch.int32
+
+
+def test_more_layers_than_one_launch_carries():
+    """70 distilled layers: chunked into launches of <= MAFED_MAX_LAYERS, totals added."""
+    n = 70
+    st, te, am = O.make_inputs(n + 1, 2, 3, 32, n_vis=256, seed=71)
+    meta = dict(modality="equal", layer_strategy="discounted", loss="mse", gamma=0.9, num_hidden_layers=n, layer=None,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    ref = O.forward_backward(st, te, am, oracle_cfg(meta))
+    out = run_product(meta, st, te, am)
+    logged = {f"task_0/distill_loss_{l}": float(v) for l, v in ref["layer_losses"].items()}
+    _check(out, ref["loss"], ref["grads"], torch.float32, logged)
