@@ -330,6 +330,53 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
         }
         const uint32_t sa = s_base + (uint32_t)r * row_bytes, ta = t_base + (uint32_t)r * row_bytes;
         float ch = 0.f, cp = 0.f, rowval = 0.f;
+        if (LOSS == MAFED_LOSS_COSINE && NCW == 8 && p.n_chunks <= 256) {
+          // cosine, rows up to 4 KB, 8-warp build only (the 16-warp default has no register room for it and
+          // hides the latency of the two-pass form better, profiles/): the lane's share of the row pair lives in
+          // registers between the statistics pass and the gradient pass
+          uint4 sv[8], tv[8];
+          float x = 0.f, y = 0.f, z = 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = lane + 32 * u;
+            if (c < p.n_chunks) {
+              sv[u] = lds_128(sa + (uint32_t)c * 16u);
+              tv[u] = lds_128(ta + (uint32_t)c * 16u);
+            } else {
+              sv[u] = make_uint4(0, 0, 0, 0);
+              tv[u] = make_uint4(0, 0, 0, 0);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float a[NE], b[NE];
+            Pack<T>::unpack(sv[u], a);
+            Pack<T>::unpack(tv[u], b);
+            accumulate<LOSS, NE>(a, b, x, y, z);
+          }
+          x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
+          const float aa = y + kCosEps, den = sqrtf(aa * (z + kCosEps));
+          ch = w * (x / den) / aa;
+          cp = w / den;
+          if (gb != nullptr) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int c = lane + 32 * u;
+              if (c >= p.n_chunks) continue;
+              float a[NE], b[NE], o[NE];
+              Pack<T>::unpack(sv[u], a);
+              Pack<T>::unpack(tv[u], b);
+              grad_elems_tma<LOSS, NE>(a, b, w, ch, cp, o);
+              stg_128(grow + (long long)c * 16, Pack<T>::pack(o), p.store_policy, spol);
+            }
+          }
+          if (FUSED && lane == 0) {
+            const float val = 1.f - x / den;
+            if (mt.mod[r] == 0) acc_text = fmaf(mt.w[r], val, acc_text);
+            else acc_vis = fmaf(mt.w[r], val, acc_vis);
+          }
+          continue;
+        }
         if (LOSS == MAFED_LOSS_COSINE) {
           float x = 0.f, y = 0.f, z = 0.f;
           for (int c = lane; c < p.n_chunks; c += 32) {
