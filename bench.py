@@ -295,6 +295,12 @@ def main():
     ap.add_argument("--no-other-workloads", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # plain `python bench.py --gpus N`: relaunch as one process per GPU (what the driver does itself)
+        os.dup2(_REAL_STDOUT.fileno(), 1)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+                                   str(29000 + os.getpid() % 2000), os.path.abspath(__file__), *sys.argv[1:]])
     if args.impl == "reference":
         if args.steps > 5:
             args.steps = 5
