@@ -14,4 +14,4 @@ timeout 300 $CMD > gpurun_out/plain3.log 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:'k_fwd_tma' -s 4 -c 1 -o gpurun_out/prof9_fwd $CMD > gpurun_out/ncu_fwd.log 2>&1
 timeout 300 $CMD > gpurun_out/plain4.log 2>&1 && \
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:'k_bwd_tma.*Li16ELi1E' -s 4 -c 1 -o gpurun_out/prof9_bwd $CMD > gpurun_out/ncu_bwd.log 2>&1
-tail -2 gpurun_out/ncu_fused.log gpurun_out/ncu_fwd.log gpurun_out/ncu_bwd.log
+for f in fused fwd bwd; do tail -n 2 gpurun_out/ncu_$f.log; done
