@@ -194,25 +194,29 @@ bool tma_geometry(const PathParams& p, int pass, TmaGeom& geo) {
 
 template <typename T, int LOSS, int NCW>
 int launch_tma(const PathParams& p, const TmaGeom& geo, int pass, cudaStream_t st) {
-  static bool attr[3] = {false, false, false};
+  // the opt-in shared-memory size is a per-device function attribute: remember it per (pass, device)
+  static unsigned attr_devices[3] = {0u, 0u, 0u};
   const DeviceInfo& dv = device_info();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned dev_bit = 1u << (dev & 31);
   const size_t dyn = (size_t)geo.stages * geo.stage_bytes;
   const int max_dyn = dv.smem_optin - 16 * 1024;
   if constexpr (LOSS == kLossL2Norm) {
     if (pass != kPassFwd) return MAFED_E_ARG;
-    if (!attr[0]) {
+    if (!(attr_devices[0] & dev_bit)) {
       cudaError_t e = cudaFuncSetAttribute(k_fwd_tma<T, LOSS, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
       if (e != cudaSuccess) return (int)e;
-      attr[0] = true;
+      attr_devices[0] |= dev_bit;
     }
-  } else if (!attr[pass]) {
+  } else if (!(attr_devices[pass] & dev_bit)) {
     cudaError_t e =
         pass == kPassFwd ? cudaFuncSetAttribute(k_fwd_tma<T, LOSS, NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn)
         : pass == kPassBwd
             ? cudaFuncSetAttribute(k_bwd_tma<T, LOSS, NCW, kBackward>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn)
             : cudaFuncSetAttribute(k_bwd_tma<T, LOSS, NCW, kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     if (e != cudaSuccess) return (int)e;
-    attr[pass] = true;
+    attr_devices[pass] |= dev_bit;
   }
   const long long total = ((p.n_rows + geo.rows - 1) / geo.rows) * p.n_layers;
   int mul = g_tune[kTuneGridMul].load();

@@ -44,3 +44,12 @@ def test_sass_is_sm100_and_uses_bulk_copies():
     assert "sm_100a" in out or "sm_100" in out
     assert "UBLKCP" in out  # cp.async.bulk (TMA engine) in the staged kernels
     assert re.search(r"LDG\.E(\.NA)?\.128", out) and "STG.E.128" in out and "LDS.128" in out
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CUDA library -> the product raises; there is no eager / CPU fallback to fall into."""
+    import pytest
+    monkeypatch.setattr(cabi, "_lib", None)
+    monkeypatch.setattr(cabi, "LIB_PATH", str(tmp_path / "libmafed_distill.so"))
+    with pytest.raises(cabi.MafedDistillError, match="no CPU / eager fallback"):
+        cabi.load()
