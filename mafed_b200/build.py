@@ -10,12 +10,12 @@ LIB_PATH = os.path.join(LIB_DIR, "libmafed_distill.so")
 SOURCES = [os.path.join(PKG, "csrc", "distill_abi.cu")]
 HEADERS = [os.path.join(PKG, "csrc", n) for n in
            ("distill_common.cuh", "distill_ldg.cuh", "distill_tma.cuh", "distill_epilogue.cuh",
-            "distill_fused.cuh", "distill_host.cuh")] + \
+            "distill_comm.cuh", "distill_host.cuh")] + \
           [os.path.join(ROOT, "include", "mafed_distill.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC", "-shared",
 ]
 
 
@@ -38,8 +38,7 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [_nvcc()] + flags + ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
                                "-o", LIB_PATH] + SOURCES
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

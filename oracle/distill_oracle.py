@@ -224,7 +224,6 @@ def closed_form(students, teachers, attention_mask, cfg: OracleConfig, grad_out:
         if cfg.cls_distillation:
             if cfg.loss != "cosine":
                 raise TypeError("cls distillation only works with the cosine loss")
-            weights = [(np.zeros_like(w_vis), 0.0)]
             wv0 = np.zeros_like(w_vis)
             wv0[:, 0] = 1.0
             mods = [(wv0, 1.0, float(bsz))]
