@@ -357,6 +357,7 @@ class _DistillFunction(torch.autograd.Function):
         return total, aux
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_total, _grad_aux):
         ln, plan = ctx.launch, ctx.plan
         if grad_total is None or ln is None or not any(ctx.needs):

@@ -289,3 +289,42 @@ def test_more_layers_than_one_launch_carries():
     out = run_product(meta, st, te, am)
     logged = {f"task_0/distill_loss_{l}": float(v) for l, v in ref["layer_losses"].items()}
     _check(out, ref["loss"], ref["grads"], torch.float32, logged)
+
+
+def test_step_is_cuda_graph_capturable():
+    """include/mafed_distill.h: no allocation / no host sync inside the ABI calls -> a step can be captured once
+    and replayed; new inputs are picked up from the same buffers."""
+    from mafed_b200.distill_op import DistillPlan, distill_backward, distill_fused
+    st, te, am = O.make_inputs(3, 3, 5, 768, n_vis=256, dtype=torch.bfloat16, seed=91)
+    cfg = O.OracleConfig(modality_strategy="equal", layer_strategy="discounted", gamma=0.5, num_hidden_layers=2,
+                         distillation_layer=None)
+    layers, coeffs, _ = O.layer_plan(cfg)
+    plan = DistillPlan(layers=layers, layer_coeffs=[float(c) for c in coeffs], modality_kind=cabi.MODW_EQUAL)
+    s = [x.cuda() for x in st[:2]]
+    t = [x.cuda() for x in te[:2]]
+    g = [torch.empty_like(x) for x in s]
+    mask = am.cuda()
+    gout = torch.ones((), device="cuda")
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(2):                                    # warm-up outside capture (function attributes etc.)
+            out, scale, ln = distill_fused(s, t, g, mask, plan, group=False)
+            distill_backward(ln, g, scale, gout, skip_if_equals=1.0)
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph):
+        out, scale, ln = distill_fused(s, t, g, mask, plan, group=False)
+        distill_backward(ln, g, scale, gout, skip_if_equals=1.0)
+    for trial in range(2):
+        if trial == 1:                                        # new data in the captured buffers
+            st2, te2, _ = O.make_inputs(3, 3, 5, 768, n_vis=256, dtype=torch.bfloat16, seed=92, teacher="independent")
+            for dst, src in zip(s + t, st2[:2] + te2[:2]):
+                dst.copy_(src)
+            st, te = st2, te2
+        graph.replay()
+        torch.cuda.synchronize()
+        ref = O.forward_backward(st, te, am, cfg)
+        assert float(out[0]) == pytest.approx(float(ref["loss"]), rel=2e-3)
+        for l in range(2):
+            assert rel_err(g[l].float().cpu(), ref["grads"][l].float()) < 2e-3
