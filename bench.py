@@ -476,8 +476,9 @@ def main():
                               "bytes_per_unit": 5 * row_bytes},
         },
         # per step: modality masks, fused kernel (scale table derived in-kernel), epilogue, backward fix-up;
-        # batch-sharded: + a prologue carrying the counts exchange (peer path) or counts/reduce kernels (NCCL)
-        "gpu_launches": args.steps * (4 if world == 1 else (5 if peer_path else 7)),
+        # batch-sharded over peer memory: the same four (exchanges inside the fused kernel and the epilogue);
+        # NCCL fallback: + counts / prologue / reduce kernels
+        "gpu_launches": args.steps * (4 if (world == 1 or peer_path) else 7),
         "exchange": "none" if world == 1 else ("nvlink peer-memory mailboxes inside the scalar-stage kernels"
                                                if peer_path else "nccl allreduce"),
         "loss": float(loss.detach()),

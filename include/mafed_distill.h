@@ -169,6 +169,17 @@ int mafed_distill_scalar_stage_comm(const mafed_shape_t* shape, const mafed_weig
                                     const int64_t* attn_mask, const void* ws, double* sums, float* out,
                                     float* bwd_scale, mafed_comm_t* comm, int comm_what, void* stream);
 
+/* mafed_distill_fused for the batch-sharded step: with `comm` (and `weights`) the exchange of the two token
+ * counts happens INSIDE the fused kernel -- CTA 0 stores this rank's counts into every peer mailbox, all
+ * CTAs wait on the local mailbox and derive the scale table -- so the step needs no prologue launch and the
+ * NVLink round trip hides behind the first tiles.  The epoch of this exchange is tracked on the host (one per
+ * call), so this entry is not CUDA-graph replayable; under capture use mafed_distill_scalar_stage_comm
+ * (prologue) + mafed_distill_fused(weights = NULL).  comm == NULL behaves like mafed_distill_fused. */
+int mafed_distill_fused_comm(const mafed_shape_t* shape, const void* const* student_ptrs,
+                             const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
+                             const mafed_weights_t* weights, float* bwd_scale, float assumed_grad_out, void* ws,
+                             mafed_comm_t* comm, void* stream);
+
 /* Gradient-norm modality importances (distillation_loss_weights.py:122-137): for every tensor of the
  * table (one per selected layer, [B, T, D]) the per-token L2 norm over D (`torch.linalg.norm(grad,
  * dim=-1)`, :131) summed per modality with the mask weights (:133-137), all layers in one pass.

@@ -30,6 +30,7 @@ EXPORTS = (
     "mafed_distill_reduce", "mafed_distill_finalize", "mafed_distill_epilogue", "mafed_distill_prologue",
     "mafed_distill_bwd", "mafed_distill_fused", "mafed_distill_modality_masks", "mafed_distill_token_norm_sums",
     "mafed_distill_set_variant", "mafed_distill_set_tuning", "mafed_distill_scalar_stage_comm",
+    "mafed_distill_fused_comm",
     "mafed_comm_handle_bytes", "mafed_comm_create", "mafed_comm_connect", "mafed_comm_status", "mafed_comm_destroy",
     "mafed_host_step_device_bytes", "mafed_host_step_create", "mafed_host_step_run", "mafed_host_step_destroy",
     "mafed_host_register", "mafed_host_unregister",
@@ -102,6 +103,8 @@ def load():
         lib.mafed_distill_bwd.argtypes = [sh, pp, pp, pp, vp, vp, vp, ctypes.POINTER(ctypes.c_float), vp]
         lib.mafed_distill_fused.restype = i32
         lib.mafed_distill_fused.argtypes = [sh, pp, pp, pp, vp, wt, vp, ctypes.c_float, vp, vp]
+        lib.mafed_distill_fused_comm.restype = i32
+        lib.mafed_distill_fused_comm.argtypes = [sh, pp, pp, pp, vp, wt, vp, ctypes.c_float, vp, vp, vp]
         lib.mafed_distill_scalar_stage_comm.restype = i32
         lib.mafed_distill_scalar_stage_comm.argtypes = [sh, wt, i32, vp, vp, vp, vp, vp, vp, i32, vp]
         lib.mafed_comm_handle_bytes.restype = i32

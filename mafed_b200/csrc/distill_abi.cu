@@ -322,6 +322,7 @@ int fill_params(const mafed_shape_t* shape, const void* const* student_ptrs, con
 struct mafed_comm {
   int world = 0;
   int rank = 0;
+  unsigned long long host_epoch = 0;   // collectives enqueued so far (mirrors the device-side counter)
   void* local = nullptr;
   void* peers[mafed::kCommMaxRanks] = {};
 };
@@ -356,6 +357,7 @@ int launch_scalar_stage(const mafed_shape_t& sh, const mafed_weights_t* w, int f
     if (comm_what == (MAFED_COMM_SUMS | MAFED_COMM_COUNTS)) { e.comm_first = 0; e.comm_count = L2 + 2; }
     else if (comm_what == MAFED_COMM_SUMS) { e.comm_first = 0; e.comm_count = L2; }
     else if (comm_what == MAFED_COMM_COUNTS) { e.comm_first = L2; e.comm_count = 2; }
+    if (e.comm_count > 0) const_cast<mafed_comm*>(comm)->host_epoch += 1;
   }
   e.ws = reinterpret_cast<const float*>(ws);
   e.mask = mask;
@@ -554,7 +556,16 @@ int mafed_distill_bwd(const mafed_shape_t* shape, const void* const* student_ptr
 int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
                         void* const* grad_ptrs, const int64_t* attn_mask, const mafed_weights_t* weights, float* bwd_scale,
                         float assumed_grad_out, void* ws, void* stream) {
+  return mafed_distill_fused_comm(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, weights, bwd_scale,
+                                  assumed_grad_out, ws, nullptr, stream);
+}
+
+int mafed_distill_fused_comm(const mafed_shape_t* shape, const void* const* student_ptrs,
+                             const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
+                             const mafed_weights_t* weights, float* bwd_scale, float assumed_grad_out, void* ws,
+                             mafed_comm_t* comm, void* stream) {
   if (!grad_ptrs || !bwd_scale || !ws) return MAFED_E_ARG;
+  if (comm != nullptr && comm->world > 1 && !weights) return MAFED_E_ARG;
   PathParams p;
   int rc = fill_params(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, p);
   if (rc) return rc;
@@ -572,9 +583,13 @@ int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_p
       p.n_vis_rows = shape->cls ? (double)shape->B : (double)shape->B * (double)shape->n_vis;
       p.bwd_scale_out = bwd_scale;
       p.w = *weights;
+      if (comm != nullptr && comm->world > 1) {   // the counts exchange rides inside the kernel
+        p.comm = comm_dev(comm);
+        p.comm_epoch = ++comm->host_epoch;
+      }
     } else {
       rc = launch_scalar_stage(*shape, weights, MAFED_STAGE_COUNTS | MAFED_STAGE_SCALE, attn_mask, nullptr, nullptr,
-                               nullptr, bwd_scale, (cudaStream_t)stream);
+                               nullptr, bwd_scale, (cudaStream_t)stream, comm, MAFED_COMM_COUNTS);
       if (rc) return rc;
     }
   }

@@ -17,19 +17,6 @@
 
 namespace mafed {
 
-constexpr int kCommMaxRanks = 16;
-constexpr int kCommSlots = 2 * kMaxLayers + 2;  // one full `sums` vector
-constexpr long long kCommTimeoutCycles = 4000000000LL;
-
-struct CommDev {
-  double* data[kCommMaxRanks];              // mailbox data region of every rank (peer-mapped; [rank] is local)
-  unsigned long long* flags[kCommMaxRanks]; // mailbox flag region of every rank
-  unsigned long long* epoch;                // local: collectives issued so far
-  int* status;                              // local: 0 ok, 1 timeout
-  int world;                                // 0 = no communicator (single rank)
-  int rank;
-};
-
 constexpr size_t kCommDataBytes = sizeof(double) * 2 * kCommMaxRanks * kCommSlots;
 constexpr size_t kCommFlagBytes = sizeof(unsigned long long) * 2 * kCommMaxRanks;
 constexpr size_t kCommMailboxBytes = kCommDataBytes + kCommFlagBytes + 64;  // + epoch + status

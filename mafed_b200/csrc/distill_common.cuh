@@ -17,6 +17,20 @@ constexpr float kCosEps = 1e-12f;  // EPSILON of ATen's cosine_embedding_loss
 constexpr int kMaxPartials = 2048;  // upper bound on CTAs writing partial sums
 constexpr int kWsHeaderFloats = 4;  // ws[0] = number of partial blocks (as int)
 
+// Peer-memory communicator as the kernels see it (see distill_comm.cuh).
+constexpr int kCommMaxRanks = 16;
+constexpr int kCommSlots = 2 * kMaxLayers + 2;  // one full `sums` vector
+constexpr long long kCommTimeoutCycles = 4000000000LL;
+
+struct CommDev {
+  double* data[kCommMaxRanks];              // mailbox data region of every rank (peer-mapped; [rank] is local)
+  unsigned long long* flags[kCommMaxRanks]; // mailbox flag region of every rank
+  unsigned long long* epoch;                // local: collectives issued so far
+  int* status;                              // local: 0 ok, 1 timeout
+  int world;                                // 0 = no communicator (single rank)
+  int rank;
+};
+
 // Kernel-parameter block shared by forward and backward kernels (passed by value, < 4 KB).
 struct PathParams {
   const void* s[kMaxLayers];
@@ -45,6 +59,9 @@ struct PathParams {
   double n_vis_rows;             // B * n_vis
   float* bwd_scale_out;          // CTA 0 publishes the table for the later backward fix-up
   mafed_weights_t w;
+  // batch-sharded one-pass step: the token counts are exchanged inside this kernel (comm.world > 1)
+  unsigned long long comm_epoch; // epoch of this exchange (host-tracked, = device epoch + 1)
+  CommDev comm;
   int load_policy;               // L2 eviction hint for student/teacher reads (CachePolicy)
   int store_policy;              // L2 eviction hint for gradient writes
 };

@@ -3,6 +3,7 @@
 // read the staged rows with conflict-free 128-bit shared loads.  One persistent CTA per SM; the ring
 // keeps up to ~190 KB per SM in flight without spending registers on it.
 #pragma once
+#include "distill_comm.cuh"
 #include "distill_common.cuh"
 
 namespace mafed {
@@ -275,12 +276,46 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) s_cnt[warp] = c;
     named_bar_sync(1, NCW * 32);
-    if ((int)threadIdx.x < p.n_layers) {
-      long long n_text = 0;
+    long long n_text_local = 0;
 #pragma unroll
-      for (int i = 0; i < NCW; ++i) n_text += s_cnt[i];
+    for (int i = 0; i < NCW; ++i) n_text_local += s_cnt[i];
+    double n_text = (double)n_text_local, n_vis_rows = p.n_vis_rows;
+    if (p.comm.world > 1) {
+      // Batch-sharded step: the two token counts are exchanged right here.  CTA 0 stores this rank's counts
+      // into every rank's mailbox and publishes the epoch; every CTA then waits on its OWN rank's mailbox
+      // (local L2) for all peers and sums in rank order.  The NVLink round trip hides behind the first tiles.
+      const CommDev& c = p.comm;
+      const unsigned long long e = p.comm_epoch;
+      const int par = (int)(e & 1ull);
+      if (blockIdx.x == 0) {
+        if ((int)threadIdx.x < 2 * c.world) {
+          const int peer = threadIdx.x >> 1, k = threadIdx.x & 1;
+          c.data[peer][((size_t)par * kCommMaxRanks + c.rank) * kCommSlots + k] = k == 0 ? n_text : n_vis_rows;
+        }
+        __threadfence_system();
+        named_bar_sync(1, NCW * 32);
+        if ((int)threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + par * kCommMaxRanks + c.rank, e);
+        if (threadIdx.x == 0) *c.epoch = e;   // keep the device-side counter of the scalar stages in step
+      }
+      if ((int)threadIdx.x < c.world) {
+        const unsigned long long* f = c.flags[c.rank] + par * kCommMaxRanks + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < e) {
+          if (clock64() - t0 > kCommTimeoutCycles) { *c.status = 1; break; }
+        }
+      }
+      named_bar_sync(1, NCW * 32);
+      const double* mine = c.data[c.rank] + (size_t)par * kCommMaxRanks * kCommSlots;
+      n_text = 0.0;
+      n_vis_rows = 0.0;
+      for (int r = 0; r < c.world; ++r) {
+        n_text += __ldcg(mine + (size_t)r * kCommSlots);
+        n_vis_rows += __ldcg(mine + (size_t)r * kCommSlots + 1);
+      }
+    }
+    if ((int)threadIdx.x < p.n_layers) {
       float st, sv;
-      backward_scales(p.w, threadIdx.x, (double)n_text, p.n_vis_rows, p.loss_kind, p.D, st, sv);
+      backward_scales(p.w, threadIdx.x, n_text, n_vis_rows, p.loss_kind, p.D, st, sv);
       s_scale[2 * threadIdx.x] = st;
       s_scale[2 * threadIdx.x + 1] = sv;
       if (blockIdx.x == 0) {

@@ -285,8 +285,19 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
         distributed, pg = resolve_group(group)
         peer = get_peer_comm(pg) if distributed else None
         if peer is not None:
-            # same three launches as the single-GPU step; the two exchanges ride inside the scalar stages
             sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
+            if not torch.cuda.is_current_stream_capturing():
+                # two launches, as on one GPU: the counts are exchanged inside the fused kernel (hidden behind its
+                # first tiles), sums + counts inside the epilogue
+                cabi.check(lib.mafed_distill_fused_comm(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr, w,
+                                                        bwd_scale.data_ptr(), fixed, ws.data_ptr(), peer.handle,
+                                                        stream), "mafed_distill_fused_comm")
+                cabi.check(lib.mafed_distill_scalar_stage_comm(
+                    ln.shape_ref, w, cabi.STAGE_REDUCE | cabi.STAGE_COUNTS | cabi.STAGE_LOSSES, ln.mask_ptr,
+                    ws.data_ptr(), sums.data_ptr(), out.data_ptr(), None, peer.handle,
+                    cabi.COMM_SUMS | cabi.COMM_COUNTS, stream), "epilogue_comm")
+                return out, bwd_scale, ln
+            # under CUDA-graph capture: device-side epochs only (prologue with the counts exchange)
             cabi.check(lib.mafed_distill_scalar_stage_comm(
                 ln.shape_ref, w, cabi.STAGE_COUNTS | cabi.STAGE_SCALE, ln.mask_ptr, None, sums.data_ptr(), None,
                 bwd_scale.data_ptr(), peer.handle, cabi.COMM_COUNTS, stream), "prologue_comm")
