@@ -328,3 +328,35 @@ def test_step_is_cuda_graph_capturable():
         assert float(out[0]) == pytest.approx(float(ref["loss"]), rel=2e-3)
         for l in range(2):
             assert rel_err(g[l].float().cpu(), ref["grads"][l].float()) < 2e-3
+
+
+def test_wandb_values_are_logged_late_without_host_sync(monkeypatch):
+    """distillation.py:165 logs task_{k}/distill_loss_{layer} per layer with .item(); here the same keys and
+    values reach W&B from a pinned buffer, one step late (or on flush_logs)."""
+    import types
+
+    from gpu_util import Out, make_method
+    from mafed_b200.methods import distillation as D
+    logged = []
+    fake = types.SimpleNamespace(run=object(), log=lambda d, *a, **k: logged.append(dict(d)))
+    monkeypatch.setattr(D, "_wandb", fake)
+    st, te, am = O.make_inputs(4, 2, 5, 128, n_vis=256, seed=95)
+    meta = dict(modality="balanced", layer_strategy="discounted", loss="mse", gamma=0.5, num_hidden_layers=3, layer=None,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    ref = O.forward_backward(st, te, am, oracle_cfg(meta))
+    fd = make_method(meta)
+    fd.task_id = 2
+    te_c = [t.cuda() for t in te]
+    fd.past_model = lambda **kw: Out(tuple(te_c))
+    leaves = [s.cuda().requires_grad_(True) for s in st]
+    fd.distill(Out(tuple(leaves)), {"attention_mask": am.cuda()})
+    torch.cuda.synchronize()
+    assert logged == []                                   # nothing forced the host to wait during the step
+    fd.distill(Out(tuple(leaves)), {"attention_mask": am.cuda()})   # the next step hands over the previous values
+    assert len(logged) == 1 and set(logged[0]) == {f"task_2/distill_loss_{l}" for l in range(3)}
+    for l in range(3):
+        assert logged[0][f"task_2/distill_loss_{l}"] == pytest.approx(float(ref["layer_losses"][l]), rel=1e-5)
+    fd.flush_logs()
+    assert len(logged) == 2 and logged[1] == pytest.approx(logged[0])
+    fd.flush_logs()
+    assert len(logged) == 2

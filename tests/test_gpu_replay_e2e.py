@@ -100,3 +100,30 @@ def test_replay_without_distillation_returns_lm_loss_only():
     fd.task_id = 0                                                   # no replay on the first task (:88)
     fd.distillation_coeff = 0.0
     assert fd.replay(model)[0] is None
+
+
+def test_training_step_aggregation_without_lightning():
+    """vqa_cont_learner.py:213-236 as a plain function: replay every `replay_interval`-th batch once task_id > 0."""
+    from mafed_b200.methods import CLMethod
+    from mafed_b200.step import backward_step, training_step_loss
+    from tiny_vl import TinyVL, make_batch
+    torch.manual_seed(0)
+    model = TinyVL().cuda()
+    fd = CLMethod["featdistill"](memory_size=8, opts=Opts(), model_type="vlpythia",
+                                 distillation_modality_weighing_strategy="balanced",
+                                 distillation_layer_weighing_strategy="discounted", distillation_layer=None,
+                                 num_hidden_layers=3, gamma=0.5)
+    fd.num_vision_tokens = 8
+    fd._update_model(model)
+    fd.mem_dataloader = [make_batch(seed=3, device="cuda")]
+    batch = make_batch(seed=4, device="cuda")
+    keys = []
+    for task_id in (0, 1):
+        fd.task_id = task_id
+        for idx in range(4):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss, key = training_step_loss(fd, model, dict(batch), idx, task_id, replay_interval=2)
+            backward_step(loss, Opts.accumulate_grad_batches)
+            keys.append(key.split("/")[1])
+    assert keys == ["train_loss"] * 4 + ["train_loss", "replay_train_loss", "train_loss", "replay_train_loss"]
+    assert fd.step == 2 and all(p.grad is not None for p in model.gpt_neox.layers[0].parameters())
