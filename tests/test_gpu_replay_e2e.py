@@ -115,7 +115,11 @@ def test_training_step_aggregation_without_lightning():
                                  num_hidden_layers=3, gamma=0.5)
     fd.num_vision_tokens = 8
     fd._update_model(model)
-    fd.mem_dataloader = [make_batch(seed=3, device="cuda")]
+    class FreshBatches:                                # a DataLoader yields a new dict per iteration
+        def __iter__(self):
+            yield make_batch(seed=3, device="cuda")
+
+    fd.mem_dataloader = FreshBatches()
     batch = make_batch(seed=4, device="cuda")
     keys = []
     for task_id in (0, 1):
