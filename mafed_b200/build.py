@@ -26,11 +26,25 @@ def _nvcc():
     return exe
 
 
+STAMP_PATH = os.path.join(LIB_DIR, "build.stamp")
+
+
+def _fingerprint():
+    """Hash of every source / header and the compile flags (mtimes do not survive a copy to another box)."""
+    import hashlib
+    h = hashlib.sha1(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        if os.path.exists(f):
+            with open(f, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
 def is_stale():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.exists(f) and os.path.getmtime(f) > t for f in SOURCES + HEADERS)
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != _fingerprint()
 
 
 def build(force=False, verbose=False):
@@ -47,6 +61,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    with open(STAMP_PATH, "w") as f:
+        f.write(_fingerprint())
     return LIB_PATH
 
 
