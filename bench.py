@@ -479,7 +479,7 @@ def main():
         # batch-sharded over peer memory: the same four (exchanges inside the fused kernel and the epilogue);
         # NCCL fallback: + counts / prologue / reduce kernels
         "gpu_launches": args.steps * (4 if (world == 1 or peer_path) else 7),
-        "exchange": "none" if world == 1 else ("nvlink peer-memory mailboxes inside the scalar-stage kernels"
+        "exchange": "none" if world == 1 else ("nvlink peer-memory mailboxes: counts inside the fused kernel, sums inside the epilogue kernel"
                                                if peer_path else "nccl allreduce"),
         "loss": float(loss.detach()),
     }
