@@ -363,6 +363,9 @@ class _DistillFunction(torch.autograd.Function):
         else:
             out, bwd_scale, ln = distill_forward(students, teachers, attn_mask, plan, group)
         ctx.launch, ctx.bwd_scale = ln, bwd_scale
+        # registered with autograd so that an in-place modification of a hidden state between forward and
+        # backward is detected (the backward / fix-up kernel would otherwise read the modified values)
+        ctx.save_for_backward(*students, *teachers)
         total, aux = out[0], out[1:]
         ctx.mark_non_differentiable(aux)
         return total, aux
@@ -373,6 +376,7 @@ class _DistillFunction(torch.autograd.Function):
         ln, plan = ctx.launch, ctx.plan
         if grad_total is None or ln is None or not any(ctx.needs):
             return (None,) * (4 + len(ctx.needs))
+        _ = ctx.saved_tensors   # version-counter check of students / teachers
         g = grad_total
         if g.dtype != torch.float32 or g.device != ln.device:
             g = g.to(device=ln.device, dtype=torch.float32)

@@ -360,3 +360,19 @@ def test_wandb_values_are_logged_late_without_host_sync(monkeypatch):
     assert len(logged) == 2 and logged[1] == pytest.approx(logged[0])
     fd.flush_logs()
     assert len(logged) == 2
+
+
+def test_inplace_modification_between_forward_and_backward_is_detected():
+    from gpu_util import Out, make_method
+    st, te, am = O.make_inputs(3, 2, 4, 64, n_vis=256, seed=97)
+    meta = dict(modality="balanced", layer_strategy="equal", loss="mse", gamma=0.5, num_hidden_layers=2, layer=None,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    fd = make_method(meta)
+    te_c = [t.cuda() for t in te]
+    fd.past_model = lambda **kw: Out(tuple(te_c))
+    base = [s.cuda().requires_grad_(True) for s in st]
+    hidden = [b * 1.0 for b in base]                       # non-leaf hidden states, as in a real model
+    loss = fd.distill(Out(tuple(hidden)), {"attention_mask": am.cuda()})
+    hidden[0].add_(1.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        loss.backward()
