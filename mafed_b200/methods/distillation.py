@@ -315,6 +315,36 @@ class FeatureDistillation(CLStrategy):
         vals = self.last_layer_losses[: len(self.last_layers)].tolist()
         return {f"task_{self.task_id}/distill_loss_{l}": v for l, v in zip(self.last_layers, vals)}
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self) -> Dict[str, object]:
+        """Strategy state that the reference keeps only in the live Python object across the task loop
+        (``train.py:207``; SURVEY 5 "checkpoint / resume"): task counter, step counter, the sampled memory
+        indices per task, the sampling RNG, and the adaptive language coefficients."""
+        coeff = getattr(self.loss_weights, "lang_coeff", None)
+        return {
+            "task_id": self.task_id,
+            "step": self.step,
+            "memory_indices": [np.asarray(ds.indices).tolist() for ds in self.datasets],
+            "rng_state": self.rng.bit_generator.state,
+            "lang_coeff": coeff.detach().cpu() if torch.is_tensor(coeff) else coeff,
+        }
+
+    def load_state_dict(self, state: Dict[str, object], datasets=None):
+        """Restore ``state_dict()``.  ``datasets`` (one per finished task, in order) lets the episodic memory be
+        rebuilt from the saved indices; the teacher snapshot itself comes from the model checkpoint
+        (``_update_model``)."""
+        self.task_id = int(state["task_id"])
+        self.step = int(state["step"])
+        self.rng.bit_generator.state = state["rng_state"]
+        coeff = state.get("lang_coeff")
+        if coeff is not None:
+            self.loss_weights.lang_coeff = coeff
+            self.loss_weights._lang_coeff_host = None
+        self._plan_cache = None
+        if datasets is not None:
+            from torch.utils.data import Subset
+            self.datasets = [Subset(ds, idx) for ds, idx in zip(datasets, state["memory_indices"])]
+
     # ------------------------------------------------------------------ between tasks
     def _update_model(self, model):
         """Freeze a copy of the just-trained model as the next task's teacher."""

@@ -173,3 +173,24 @@ def test_update_memory_and_model_like_reference():
     assert sorted(sum(seen, [])) == sorted(x for ds in fd.datasets for x in
                                            [int(ds.dataset[i]["input_ids"]) for i in ds.indices])
     assert fd._next_memory_batch()["input_ids"].numel() == 4 and fd._mem_epoch == 1
+
+
+def test_strategy_state_roundtrip():
+    """Checkpoint / resume of the strategy state the reference keeps only in the live object."""
+    import numpy as np
+    kw = dict(distillation_modality_weighing_strategy="adaptive", distillation_layer_weighing_strategy="equal",
+              distillation_layer=None, num_hidden_layers=2)
+    fd = FeatureDistillation(8, Opts(), "vlpythia", **kw)
+    fd.num_workers = 0
+    fd.data_hooks = (_collate, lambda loader: loader)
+    fd._update_memory(_ToyDataset(50))
+    fd.task_id, fd.step = 1, 17
+    fd.loss_weights.lang_coeff = torch.tensor([0.3, 0.7])
+    state = fd.state_dict()
+    nxt = fd.rng.choice(np.arange(100), 5, replace=False)
+    other = FeatureDistillation(8, Opts(), "vlpythia", **kw)
+    other.load_state_dict(state, datasets=[_ToyDataset(50)])
+    assert (other.task_id, other.step) == (1, 17)
+    assert sorted(other.datasets[0].indices) == sorted(fd.datasets[0].indices)
+    assert other.loss_weights.kernel_tables()[2] == pytest.approx([0.3, 0.7])
+    assert (other.rng.choice(np.arange(100), 5, replace=False) == nxt).all()   # sampling continues identically
