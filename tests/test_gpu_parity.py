@@ -376,3 +376,39 @@ def test_inplace_modification_between_forward_and_backward_is_detected():
     hidden[0].add_(1.0)
     with pytest.raises(RuntimeError, match="modified by an inplace operation"):
         loss.backward()
+
+
+def test_two_forwards_then_one_backward_and_side_stream():
+    """Two distillation losses summed before a single backward (separate autograd nodes keep separate state);
+    then the same step on a non-default stream."""
+    from gpu_util import Out, make_method
+    meta = dict(modality="equal", layer_strategy="discounted", loss="mse", gamma=0.5, num_hidden_layers=2, layer=None,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    sets = [O.make_inputs(3, 2, 5, 256, n_vis=256, seed=s, dtype=torch.bfloat16) for s in (101, 102)]
+    refs = [O.forward_backward(st, te, am, oracle_cfg(meta), grad_out=0.5) for st, te, am in sets]
+    fd = make_method(meta)
+    leaves, total = [], 0.0
+    for st, te, am in sets:
+        te_c = [t.cuda() for t in te]
+        fd.past_model = lambda te_c=te_c, **kw: Out(tuple(te_c))
+        lv = [s.cuda().requires_grad_(True) for s in st]
+        leaves.append(lv)
+        total = total + fd.distill(Out(tuple(lv)), {"attention_mask": am.cuda()})
+    (0.5 * total).backward()
+    torch.cuda.synchronize()
+    assert float(total) == pytest.approx(float(refs[0]["loss"]) + float(refs[1]["loss"]), rel=2e-3)
+    for lv, ref in zip(leaves, refs):
+        for l in range(2):
+            assert rel_err(lv[l].grad.float().cpu(), ref["grads"][l].float()) < 2e-3
+    # non-default stream
+    side = torch.cuda.Stream()
+    st, te, am = sets[0]
+    with torch.cuda.stream(side):
+        te_c = [t.cuda() for t in te]
+        fd.past_model = lambda **kw: Out(tuple(te_c))
+        lv = [s.cuda().requires_grad_(True) for s in st]
+        loss = fd.distill(Out(tuple(lv)), {"attention_mask": am.cuda()})
+        (0.5 * loss).backward()
+    side.synchronize()
+    for l in range(2):
+        assert rel_err(lv[l].grad.float().cpu(), refs[0]["grads"][l].float()) < 2e-3
