@@ -448,6 +448,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dt,
         "data": "synthetic", "config": workload_config(wl, n_gpus),
+        "arithmetic": f"{dt} hidden states widened exactly to fp32; fp32 accumulation, fp64 final reduction; "
+                      f"gradients rounded once to {dt}",
         "mode": "one-pass (loss sums + gradients from a single read of student and teacher; 3*D*e bytes per "
                 "token*layer; upstream gradient checked on the device in backward)",
         "roofline": {"bound": "hbm", "kernel": "k_bwd_* <kFused> (+ prologue/epilogue scalar stages): 2 reads + 1 write",
