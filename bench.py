@@ -359,7 +359,7 @@ def main():
     def two_pass_step(ev=None):
         if ev:
             ev[0].record()
-        out, scale, ln = distill_forward(st, te, am, plan, group=None)      # fwd kernel + epilogue
+        out, scale, ln = distill_forward(st, te, am, plan, group=None)      # fwd kernel (losses in its last CTA)
         if ev:
             ev[1].record()
         distill_backward(ln, grads, scale, gout)                            # bwd kernel
@@ -370,7 +370,7 @@ def main():
     def one_pass_step(ev=None):
         if ev:
             ev[0].record()
-        out, scale, ln = distill_fused(st, te, grads, am, plan, group=None)  # prologue + fused kernel + epilogue
+        out, scale, ln = distill_fused(st, te, grads, am, plan, group=None)  # the whole step: one launch
         if ev:
             ev[1].record()
         distill_backward(ln, grads, scale, gout, skip_if_equals=plan.assumed_grad_out)  # fix-up: returns at once
@@ -452,7 +452,8 @@ def main():
                       f"gradients rounded once to {dt}",
         "mode": "one-pass (loss sums + gradients from a single read of student and teacher; 3*D*e bytes per "
                 "token*layer; upstream gradient checked on the device in backward)",
-        "roofline": {"bound": "hbm", "kernel": "k_bwd_* <kFused> (+ prologue/epilogue scalar stages): 2 reads + 1 write",
+        "roofline": {"bound": "hbm", "kernel": "k_bwd_tma<kFused> (whole step: masks, scale table, sums, gradients, losses): "
+                                                "2 reads + 1 write",
                      "achieved": gbs(fused_bytes, fused_ms), "peak": peak, "unit": "GB/s",
                      "frac": gbs(fused_bytes, fused_ms) / peak, "traffic": measured_traffic(wl), "peak_source": peak_src,
                      "bytes_per_launch": fused_bytes, "bytes_per_unit": 3 * row_bytes, "ms_per_launch": fused_ms,
@@ -467,7 +468,7 @@ def main():
             "note": "north_star's two-kernel form (fused forward, then fused backward): 5*D*e bytes per token*layer",
             "value": units_per_step / (two_ms * 1e-3), "ms_per_step": two_ms,
             "kernel_value": units_per_step / (two_raw_ms / args.steps * 1e-3),
-            "roofline_fwd": {"kernel": "k_fwd_* + epilogue: 2 reads", "achieved": gbs(fwd_bytes, fwd_ms), "unit": "GB/s",
+            "roofline_fwd": {"kernel": "k_fwd_tma (losses + scale table in its last CTA): 2 reads", "achieved": gbs(fwd_bytes, fwd_ms), "unit": "GB/s",
                              "frac": gbs(fwd_bytes, fwd_ms) / peak, "bytes_per_launch": fwd_bytes, "ms_per_launch": fwd_ms},
             "roofline_bwd": {"kernel": "k_bwd_* <kBackward>: 2 reads + 1 write", "achieved": gbs(bwd_bytes, bwd_ms),
                              "unit": "GB/s", "frac": gbs(bwd_bytes, bwd_ms) / peak, "bytes_per_launch": bwd_bytes,
@@ -477,12 +478,12 @@ def main():
                               "frac_of_nominal_8000": gbs(fwd_bytes + bwd_bytes, two_ms) / 8000.0,
                               "bytes_per_unit": 5 * row_bytes},
         },
-        # per step: modality masks, fused kernel (scale table derived in-kernel), epilogue, backward fix-up;
-        # batch-sharded over peer memory: the same four (exchanges inside the fused kernel and the epilogue);
-        # NCCL fallback: + counts / prologue / reduce kernels
-        "gpu_launches": args.steps * (4 if (world == 1 or peer_path) else 7),
-        "exchange": "none" if world == 1 else ("nvlink peer-memory mailboxes: counts inside the fused kernel, sums inside the epilogue kernel"
-                                               if peer_path else "nccl allreduce"),
+        # per step: the fused kernel (modality masks, scale table, loss sums + gradients, and the loss algebra in its
+        # last CTA) and the backward fix-up; batch-sharded over peer memory: the same two (both exchanges inside the
+        # fused kernel); NCCL fallback: masks, counts, prologue, fused, reduce, finalize, fix-up
+        "gpu_launches": args.steps * (2 if (world == 1 or peer_path) else 7),
+        "exchange": "none" if world == 1 else ("nvlink peer-memory mailboxes inside the fused kernel: counts at its start, "
+                                               "sums in its last CTA" if peer_path else "nccl allreduce"),
         "loss": float(loss.detach()),
     }
     line["clocks"] = sampler.summary()

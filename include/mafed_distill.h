@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MAFED_ABI_VERSION 2
+#define MAFED_ABI_VERSION 3
 #define MAFED_MAX_LAYERS 64
 
 enum { MAFED_F32 = 0, MAFED_BF16 = 1, MAFED_F16 = 2 };
@@ -179,6 +179,29 @@ int mafed_distill_fused_comm(const mafed_shape_t* shape, const void* const* stud
                              const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
                              const mafed_weights_t* weights, float* bwd_scale, float assumed_grad_out, void* ws,
                              mafed_comm_t* comm, void* stream);
+
+/* ---- the whole step as ONE call (what mafed_b200/distill_op.py uses) -------------------------------------
+ * mafed_distill_step = [mafed_distill_modality_masks] + mafed_distill_fused(_comm) + the LOSSES stage, i.e. all of
+ * FeatureDistillation.distill (distillation.py:105-166) plus the backward of its autograd graph.  For shapes the
+ * TMA-ring kernel takes (rows <= 32 KB, 16-byte aligned) and masks of <= 16 Ki entries it is ONE kernel launch:
+ * every CTA derives the gradient scale itself, all CTAs together write the two modality masks, and the CTA that
+ * finishes LAST reduces the per-CTA partial sums in fixed order (bit-reproducible) and forms the losses -- with a
+ * communicator it also exchanges the 2L sums with the peers there.  Other shapes run the same step as the
+ * separate launches above.  out[1+3L] as in LOSSES; bwd_scale[2L] is written for the later fix-up
+ * (mafed_distill_bwd with skip_if_equals); sums (optional single-rank, required with comm) receives the global
+ * [2L+2] vector; lang_mask / image_mask (both or neither, int64 [B, T]) are optional.  Like
+ * mafed_distill_fused_comm the sharded form tracks its epochs on the host (not CUDA-graph replayable).
+ * mafed_distill_fwd_step is the two-pass form's first half: mafed_distill_fwd + REDUCE|COUNTS|LOSSES|SCALE in
+ * one launch (sharded: sums and counts exchanged in the tail on the device-side epoch counter, graph-safe). */
+int mafed_distill_step(const mafed_shape_t* shape, const void* const* student_ptrs,
+                       const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
+                       const mafed_weights_t* weights, float assumed_grad_out, void* ws, float* out,
+                       float* bwd_scale, double* sums, int64_t* lang_mask, int64_t* image_mask,
+                       mafed_comm_t* comm, void* stream);
+int mafed_distill_fwd_step(const mafed_shape_t* shape, const void* const* student_ptrs,
+                           const void* const* teacher_ptrs, const int64_t* attn_mask,
+                           const mafed_weights_t* weights, void* ws, float* out, float* bwd_scale, double* sums,
+                           mafed_comm_t* comm, void* stream);
 
 /* Gradient-norm modality importances (distillation_loss_weights.py:122-137): for every tensor of the
  * table (one per selected layer, [B, T, D]) the per-token L2 norm over D (`torch.linalg.norm(grad,

@@ -14,13 +14,13 @@ LOSS_MSE, LOSS_COSINE = 0, 1
 MODW_EQUAL, MODW_TABLE, MODW_CLS, MODW_TEXT_ONLY = 0, 1, 2, 3
 VARIANT_DEFAULT, VARIANT_LDG, VARIANT_TMA = 0, 1, 2
 STAGE_REDUCE, STAGE_COUNTS, STAGE_LOSSES, STAGE_SCALE = 1, 2, 4, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 # keys of mafed_distill_set_tuning (benchmark knobs); the first three are per pass: key + PASS_*
 PASS_FWD, PASS_BWD, PASS_FUSED = 0, 1, 2
 TUNE_TMA_STAGES, TUNE_TMA_ROWS, TUNE_VARIANT = 0, 3, 6
 TUNE_TMA_WARPS, TUNE_LDG_BLOCKS_PER_SM, TUNE_BWD_FORWARD_ORDER, TUNE_GRID_MUL = 9, 10, 11, 12
 TUNE_LOAD_POLICY, TUNE_STORE_POLICY = 13, 14   # 0 none, 1 evict_first, 2 evict_last, 3 evict_normal
-N_TUNE_KEYS = 16
+N_TUNE_KEYS = 18
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmafed_distill.so")
 
@@ -30,13 +30,14 @@ EXPORTS = (
     "mafed_distill_reduce", "mafed_distill_finalize", "mafed_distill_epilogue", "mafed_distill_prologue",
     "mafed_distill_bwd", "mafed_distill_fused", "mafed_distill_modality_masks", "mafed_distill_token_norm_sums",
     "mafed_distill_set_variant", "mafed_distill_set_tuning", "mafed_distill_scalar_stage_comm",
-    "mafed_distill_fused_comm",
+    "mafed_distill_fused_comm", "mafed_distill_step", "mafed_distill_fwd_step",
     "mafed_comm_handle_bytes", "mafed_comm_create", "mafed_comm_connect", "mafed_comm_status", "mafed_comm_destroy",
     "mafed_host_step_device_bytes", "mafed_host_step_create", "mafed_host_step_run", "mafed_host_step_destroy",
     "mafed_host_register", "mafed_host_unregister",
 )
 COMM_SUMS, COMM_COUNTS = 1, 2
 TUNE_NO_PDL = 15
+TUNE_NO_INLINE_SCALE, TUNE_NO_TAIL = 16, 17   # 1: separate prologue launch / separate epilogue launch
 
 
 class Shape(ctypes.Structure):
@@ -105,6 +106,10 @@ def load():
         lib.mafed_distill_fused.argtypes = [sh, pp, pp, pp, vp, wt, vp, ctypes.c_float, vp, vp]
         lib.mafed_distill_fused_comm.restype = i32
         lib.mafed_distill_fused_comm.argtypes = [sh, pp, pp, pp, vp, wt, vp, ctypes.c_float, vp, vp, vp]
+        lib.mafed_distill_step.restype = i32
+        lib.mafed_distill_step.argtypes = [sh, pp, pp, pp, vp, wt, ctypes.c_float, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.mafed_distill_fwd_step.restype = i32
+        lib.mafed_distill_fwd_step.argtypes = [sh, pp, pp, vp, wt, vp, vp, vp, vp, vp, vp]
         lib.mafed_distill_scalar_stage_comm.restype = i32
         lib.mafed_distill_scalar_stage_comm.argtypes = [sh, wt, i32, vp, vp, vp, vp, vp, vp, i32, vp]
         lib.mafed_comm_handle_bytes.restype = i32

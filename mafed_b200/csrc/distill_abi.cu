@@ -22,7 +22,7 @@ std::atomic<int> g_tune[24] = {};  // experiment knobs, see mafed_distill_set_tu
 // per-pass keys: base + pass (fwd, bwd, fused)
 enum TuneKey { kTuneTmaStages = 0, kTuneTmaRows = 3, kTuneVariant = 6, kTuneTmaWarps = 9, kTuneLdgBlocksPerSm = 10,
                kTuneBwdForward = 11, kTuneGridMul = 12, kTuneLoadPolicy = 13, kTuneStorePolicy = 14, kTuneNoPdl = 15,
-               kTuneNoInlineScale = 16 };
+               kTuneNoInlineScale = 16, kTuneNoTail = 17 };
 
 // Launch with programmatic dependent launch enabled: the kernel may start its prologue while its
 // predecessor in the stream is finishing; all kernels here call griddepcontrol.wait before touching
@@ -97,6 +97,27 @@ void fill_geometry(const mafed_shape_t& sh, PathParams& p) {
 bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 bool needs_mask(const mafed_shape_t& sh) { return !sh.cls && sh.T > sh.n_vis; }
+long long mask_entries(const mafed_shape_t& sh) { return needs_mask(sh) ? (long long)sh.B * (sh.T - sh.n_vis) : 0; }
+double vis_rows(const mafed_shape_t& sh) { return sh.cls ? (double)sh.B : (double)sh.B * (double)sh.n_vis; }
+
+// Arrival counters of the in-kernel tail (distill_tma.cuh).  A counter is zero whenever no kernel is using it
+// (the last CTA resets it), so launches take them round-robin: two kernels can only share one if 256 tailed
+// launches are in flight at once on one device, and each of them is a persistent whole-GPU kernel.
+constexpr unsigned kDoneSlots = 256;
+__device__ unsigned int g_tail_done[kDoneSlots];
+std::atomic<unsigned> g_tail_next{0};
+
+unsigned int* next_tail_counter() {
+  static unsigned int* base[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (base[dev] == nullptr) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_tail_done) != cudaSuccess) return nullptr;
+    base[dev] = reinterpret_cast<unsigned int*>(p);
+  }
+  return base[dev] + (g_tail_next.fetch_add(1) % kDoneSlots);
+}
 
 // ---------------------------------------------------------------- launch helpers
 template <typename K>
@@ -354,25 +375,87 @@ int launch_scalar_stage(const mafed_shape_t& sh, const mafed_weights_t* w, int f
   e.comm = comm_dev(comm);
   if (e.comm.world > 1) {
     const int L2 = 2 * sh.n_layers;
-    if (comm_what == (MAFED_COMM_SUMS | MAFED_COMM_COUNTS)) { e.comm_first = 0; e.comm_count = L2 + 2; }
-    else if (comm_what == MAFED_COMM_SUMS) { e.comm_first = 0; e.comm_count = L2; }
-    else if (comm_what == MAFED_COMM_COUNTS) { e.comm_first = L2; e.comm_count = 2; }
-    if (e.comm_count > 0) const_cast<mafed_comm*>(comm)->host_epoch += 1;
+    if (comm_what == (MAFED_COMM_SUMS | MAFED_COMM_COUNTS)) { e.a.comm_first = 0; e.a.comm_count = L2 + 2; }
+    else if (comm_what == MAFED_COMM_SUMS) { e.a.comm_first = 0; e.a.comm_count = L2; }
+    else if (comm_what == MAFED_COMM_COUNTS) { e.a.comm_first = L2; e.a.comm_count = 2; }
+    if (e.a.comm_count > 0) const_cast<mafed_comm*>(comm)->host_epoch += 1;
   }
-  e.ws = reinterpret_cast<const float*>(ws);
-  e.mask = mask;
-  e.sums = sums;
-  e.out = out;
-  e.bwd_scale = bwd_scale;
-  e.n_mask = needs_mask(sh) ? (long long)sh.B * (sh.T - sh.n_vis) : 0;
-  e.n_vis_rows = sh.cls ? (double)sh.B : (double)sh.B * (double)sh.n_vis;
-  e.n_layers = sh.n_layers;
-  e.D = sh.D;
-  e.loss_kind = sh.loss_kind;
-  e.flags = flags;
+  e.a.ws = reinterpret_cast<const float*>(ws);
+  e.a.mask = mask;
+  e.a.sums = sums;
+  e.a.out = out;
+  e.a.bwd_scale = bwd_scale;
+  e.a.n_mask = mask_entries(sh);
+  e.a.n_vis_rows = vis_rows(sh);
+  e.a.n_layers = sh.n_layers;
+  e.a.D = sh.D;
+  e.a.loss_kind = sh.loss_kind;
+  e.a.flags = flags;
   if (w != nullptr) e.w = *w;
   launch_pdl(k_epilogue, 1, kEpiThreads, 0, st, e);
   return (int)cudaPeekAtLastError();
+}
+
+// What mafed_distill_step wants produced besides the gradients; with it the fused kernel may run the loss
+// algebra (and the modality masks) itself.
+struct StepTail {
+  float* out;
+  double* sums;
+  int64_t* lang_mask;
+  int64_t* image_mask;
+};
+
+int fused_impl(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
+               void* const* grad_ptrs, const int64_t* attn_mask, const mafed_weights_t* weights, float* bwd_scale,
+               float assumed_grad_out, void* ws, mafed_comm* comm, void* stream, const StepTail* tail, bool* folded) {
+  if (!grad_ptrs || !bwd_scale || !ws) return MAFED_E_ARG;
+  if (comm != nullptr && comm->world > 1 && (!weights || comm->world > kCommMaxRanks)) return MAFED_E_ARG;
+  PathParams p;
+  int rc = fill_params(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, p);
+  if (rc) return rc;
+  p.bwd_scale = bwd_scale;
+  p.fixed_gout = assumed_grad_out;
+  p.ws = reinterpret_cast<float*>(ws);
+  if (weights != nullptr) {
+    // single-rank step: the scale table is this call's business.  Small masks: every CTA of the TMA kernel
+    // derives it itself while its first tiles are in flight; otherwise one prologue launch.
+    const long long n_mask = mask_entries(*shape);
+    if (n_mask <= 16384 && !g_tune[kTuneNoInlineScale].load() && uses_tma(*shape, p, kPassFused)) {
+      p.inline_scale = 1;
+      p.loss_kind = shape->loss_kind;
+      p.n_mask = n_mask;
+      p.n_vis_rows = vis_rows(*shape);
+      p.bwd_scale_out = bwd_scale;
+      p.w = *weights;
+      const bool sharded = comm != nullptr && comm->world > 1;
+      if (sharded) {   // the counts exchange rides inside the kernel
+        p.comm = comm_dev(comm);
+        p.comm_epoch = ++comm->host_epoch;
+      }
+      unsigned int* done = nullptr;
+      if (tail != nullptr && !g_tune[kTuneNoTail].load()) done = next_tail_counter();
+      if (done != nullptr) {
+        // the last CTA to finish reduces the partials and forms the losses (and exchanges the sums with the peers):
+        // the whole step is this one launch
+        p.tail_flags = kEpiReduce | kEpiLosses;
+        p.tail_done = done;
+        p.tail_out = tail->out;
+        p.tail_sums = tail->sums;
+        p.lang_mask_out = tail->lang_mask;
+        p.image_mask_out = tail->image_mask;
+        if (sharded) {
+          p.tail_comm = 1;
+          ++comm->host_epoch;   // the sums exchange is epoch comm_epoch + 1
+        }
+        if (folded != nullptr) *folded = true;
+      }
+    } else {
+      rc = launch_scalar_stage(*shape, weights, MAFED_STAGE_COUNTS | MAFED_STAGE_SCALE, attn_mask, nullptr, nullptr,
+                               nullptr, bwd_scale, (cudaStream_t)stream, comm, MAFED_COMM_COUNTS);
+      if (rc) return rc;
+    }
+  }
+  return dispatch(*shape, p, kPassFused, (cudaStream_t)stream);
 }
 
 }  // namespace
@@ -556,44 +639,79 @@ int mafed_distill_bwd(const mafed_shape_t* shape, const void* const* student_ptr
 int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
                         void* const* grad_ptrs, const int64_t* attn_mask, const mafed_weights_t* weights, float* bwd_scale,
                         float assumed_grad_out, void* ws, void* stream) {
-  return mafed_distill_fused_comm(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, weights, bwd_scale,
-                                  assumed_grad_out, ws, nullptr, stream);
+  return fused_impl(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, weights, bwd_scale, assumed_grad_out, ws,
+                    nullptr, stream, nullptr, nullptr);
 }
 
 int mafed_distill_fused_comm(const mafed_shape_t* shape, const void* const* student_ptrs,
                              const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
                              const mafed_weights_t* weights, float* bwd_scale, float assumed_grad_out, void* ws,
                              mafed_comm_t* comm, void* stream) {
-  if (!grad_ptrs || !bwd_scale || !ws) return MAFED_E_ARG;
-  if (comm != nullptr && comm->world > 1 && !weights) return MAFED_E_ARG;
-  PathParams p;
-  int rc = fill_params(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, p);
+  return fused_impl(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, weights, bwd_scale, assumed_grad_out, ws,
+                    comm, stream, nullptr, nullptr);
+}
+
+int mafed_distill_step(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
+                       void* const* grad_ptrs, const int64_t* attn_mask, const mafed_weights_t* weights,
+                       float assumed_grad_out, void* ws, float* out, float* bwd_scale, double* sums,
+                       int64_t* lang_mask, int64_t* image_mask, mafed_comm_t* comm, void* stream) {
+  if (!weights || !out) return MAFED_E_ARG;
+  if ((lang_mask == nullptr) != (image_mask == nullptr)) return MAFED_E_ARG;
+  const bool sharded = comm != nullptr && comm->world > 1;
+  if (sharded && !sums) return MAFED_E_ARG;
+  int rc = check_shape(shape);
   if (rc) return rc;
-  p.bwd_scale = bwd_scale;
-  p.fixed_gout = assumed_grad_out;
-  p.ws = reinterpret_cast<float*>(ws);
-  if (weights != nullptr) {
-    // single-rank step: the scale table is this call's business.  Small masks: every CTA of the TMA kernel
-    // derives it itself while its first tiles are in flight; otherwise one prologue launch.
-    const long long n_mask = needs_mask(*shape) ? (long long)shape->B * (shape->T - shape->n_vis) : 0;
-    if (n_mask <= 16384 && !g_tune[kTuneNoInlineScale].load() && uses_tma(*shape, p, kPassFused)) {
-      p.inline_scale = 1;
-      p.loss_kind = shape->loss_kind;
-      p.n_mask = n_mask;
-      p.n_vis_rows = shape->cls ? (double)shape->B : (double)shape->B * (double)shape->n_vis;
-      p.bwd_scale_out = bwd_scale;
-      p.w = *weights;
-      if (comm != nullptr && comm->world > 1) {   // the counts exchange rides inside the kernel
-        p.comm = comm_dev(comm);
-        p.comm_epoch = ++comm->host_epoch;
-      }
-    } else {
-      rc = launch_scalar_stage(*shape, weights, MAFED_STAGE_COUNTS | MAFED_STAGE_SCALE, attn_mask, nullptr, nullptr,
-                               nullptr, bwd_scale, (cudaStream_t)stream, comm, MAFED_COMM_COUNTS);
-      if (rc) return rc;
-    }
+  if (lang_mask != nullptr && shape->cls) return MAFED_E_ARG;
+  StepTail tail = {out, sums, lang_mask, image_mask};
+  bool folded = false;
+  rc = fused_impl(shape, student_ptrs, teacher_ptrs, grad_ptrs, attn_mask, weights, bwd_scale, assumed_grad_out, ws,
+                  comm, stream, &tail, &folded);
+  if (rc || folded) return rc;
+  // not a single-launch shape (rows > 32 KB, unaligned tensors, a mask of more than 16 Ki entries): same step as
+  // separate launches
+  if (lang_mask != nullptr) {
+    rc = mafed_distill_modality_masks(shape, attn_mask, lang_mask, image_mask, stream);
+    if (rc) return rc;
   }
-  return dispatch(*shape, p, kPassFused, (cudaStream_t)stream);
+  const int flags = MAFED_STAGE_REDUCE | MAFED_STAGE_COUNTS | MAFED_STAGE_LOSSES;
+  return launch_scalar_stage(*shape, weights, flags, attn_mask, ws, sums, out, nullptr, (cudaStream_t)stream,
+                             sharded ? comm : nullptr, MAFED_COMM_SUMS | MAFED_COMM_COUNTS);
+}
+
+int mafed_distill_fwd_step(const mafed_shape_t* shape, const void* const* student_ptrs,
+                           const void* const* teacher_ptrs, const int64_t* attn_mask, const mafed_weights_t* weights,
+                           void* ws, float* out, float* bwd_scale, double* sums, mafed_comm_t* comm, void* stream) {
+  if (!weights || !out || !ws) return MAFED_E_ARG;
+  const bool sharded = comm != nullptr && comm->world > 1;
+  if (sharded && (!sums || comm->world > kCommMaxRanks)) return MAFED_E_ARG;
+  PathParams p;
+  int rc = fill_params(shape, student_ptrs, teacher_ptrs, nullptr, attn_mask, p);
+  if (rc) return rc;
+  p.ws = reinterpret_cast<float*>(ws);
+  const int flags = MAFED_STAGE_REDUCE | MAFED_STAGE_COUNTS | MAFED_STAGE_LOSSES | (bwd_scale ? MAFED_STAGE_SCALE : 0);
+  unsigned int* done = nullptr;
+  if (!g_tune[kTuneNoTail].load() && uses_tma(*shape, p, kPassFwd)) done = next_tail_counter();
+  if (done != nullptr) {
+    p.tail_flags = flags;
+    p.tail_done = done;
+    p.tail_out = out;
+    p.tail_sums = sums;
+    p.tail_bwd_scale = bwd_scale;
+    p.loss_kind = shape->loss_kind;
+    p.n_mask = mask_entries(*shape);
+    p.n_vis_rows = vis_rows(*shape);
+    p.w = *weights;
+    if (sharded) {   // sums + counts exchange inside the tail, on the device-side epoch counter
+      p.comm = comm_dev(comm);
+      p.tail_comm = 1;
+      comm->host_epoch += 1;
+    }
+    return dispatch(*shape, p, kPassFwd, (cudaStream_t)stream);
+  }
+  rc = dispatch(*shape, p, kPassFwd, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_scalar_stage(*shape, weights, flags, attn_mask, ws, sums, out, bwd_scale, (cudaStream_t)stream,
+                             sharded ? comm : nullptr, MAFED_COMM_SUMS | MAFED_COMM_COUNTS);
 }
 
 int mafed_distill_modality_masks(const mafed_shape_t* shape, const int64_t* attn_mask, int64_t* lang_mask,
@@ -686,8 +804,8 @@ int mafed_host_step_run(mafed_host_step_t* h, const mafed_weights_t* weights, co
     const void* tp[1] = {h->d_t[l]};
     void* gp[1] = {h->d_g[l]};
     char* ws = h->d_ws + (size_t)l * h->ws_bytes;
-    int rc = mafed_distill_fused(&one, sp, tp, gp, h->d_mask, &w, h->d_scale + 2 * l, grad_out, ws, h->s_run);
-    if (!rc) rc = mafed_distill_epilogue(&one, &w, h->d_mask, ws, nullptr, h->d_out + 4 * l, nullptr, h->s_run);
+    int rc = mafed_distill_step(&one, sp, tp, gp, h->d_mask, &w, grad_out, ws, h->d_out + 4 * l, h->d_scale + 2 * l,
+                                nullptr, nullptr, nullptr, nullptr, h->s_run);
     if (rc) return rc;
     cudaEventRecord(h->ev_run[l], h->s_run);
     cudaStreamWaitEvent(h->s_out, h->ev_run[l], 0);

@@ -30,40 +30,58 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// In-place SUM-allreduce of vals[0..n) (shared memory) across the communicator; whole CTA participates.
-__device__ __forceinline__ void peer_allreduce(const CommDev& c, double* vals, int n) {
+// How the threads taking part in a scalar stage synchronise: the whole CTA (stand-alone k_epilogue) or the
+// consumer warps of a streaming kernel through a named barrier (the in-kernel tail, whose producer warp has
+// already exited).
+struct SyncCta {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+template <int NT>
+struct SyncNamed {
+  __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, %0;" :: "n"(NT) : "memory"); }
+};
+
+// In-place SUM-allreduce of vals[0..n) (shared memory) across the communicator; threads tid = 0..NT-1 take
+// part.  `epoch` = 0: take the next epoch from the device-side counter (CUDA-graph safe); otherwise the
+// host-tracked epoch of this exchange (the counter is set to it).
+template <int NT, typename Sync>
+__device__ __forceinline__ void peer_allreduce(const CommDev& c, double* vals, int n, int tid, Sync sync,
+                                               unsigned long long epoch = 0ull) {
   __shared__ unsigned long long s_epoch;
-  __syncthreads();
-  if (threadIdx.x == 0) s_epoch = ++(*c.epoch);
-  __syncthreads();
+  sync();
+  if (tid == 0) {
+    if (epoch == 0ull) s_epoch = ++(*c.epoch);
+    else { s_epoch = epoch; *c.epoch = epoch; }
+  }
+  sync();
   const unsigned long long e = s_epoch;
   const int par = (int)(e & 1ull);
   // 1. scatter my vector into my slot of every mailbox
-  for (int i = threadIdx.x; i < n * c.world; i += blockDim.x) {
+  for (int i = tid; i < n * c.world; i += NT) {
     const int peer = i / n, k = i - peer * n;
     c.data[peer][((size_t)par * kCommMaxRanks + c.rank) * kCommSlots + k] = vals[k];
   }
   __threadfence_system();
-  __syncthreads();
+  sync();
   // 2. publish
-  if ((int)threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + par * kCommMaxRanks + c.rank, e);
+  if (tid < c.world) st_release_sys(c.flags[tid] + par * kCommMaxRanks + c.rank, e);
   // 3. wait for everybody's vector to land in my mailbox
-  if ((int)threadIdx.x < c.world) {
-    const unsigned long long* f = c.flags[c.rank] + par * kCommMaxRanks + threadIdx.x;
+  if (tid < c.world) {
+    const unsigned long long* f = c.flags[c.rank] + par * kCommMaxRanks + tid;
     const long long t0 = clock64();
     while (ld_acquire_sys(f) < e) {
       if (clock64() - t0 > kCommTimeoutCycles) { *c.status = 1; break; }
     }
   }
-  __syncthreads();
+  sync();
   // 4. reduce in rank order (identical on every rank)
   const double* mine = c.data[c.rank] + (size_t)par * kCommMaxRanks * kCommSlots;
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+  for (int k = tid; k < n; k += NT) {
     double acc = 0.0;
     for (int r = 0; r < c.world; ++r) acc += __ldcg(mine + (size_t)r * kCommSlots + k);  // L2: peers wrote it
     vals[k] = acc;
   }
-  __syncthreads();
+  sync();
 }
 
 }  // namespace mafed

@@ -64,6 +64,17 @@ struct PathParams {
   CommDev comm;
   int load_policy;               // L2 eviction hint for student/teacher reads (CachePolicy)
   int store_policy;              // L2 eviction hint for gradient writes
+  // In-kernel tail (TMA kernels): the last CTA to finish runs the scalar stage on the partial sums, so the step
+  // needs no epilogue launch.  Needs w / loss_kind / n_mask / n_vis_rows above (and comm for a sharded step).
+  int tail_flags;                // 0: no tail; else EpiFlags of the stage to run
+  int tail_comm;                 // 1: allreduce the sums (+ counts when computed in the tail) over the peer mailboxes
+  unsigned int* tail_done;       // arrival counter: zero on entry, reset by the last CTA
+  double* tail_sums;             // optional [2L + 2] copy of the (global) sums and counts
+  float* tail_out;               // [1 + 3L] losses
+  float* tail_bwd_scale;         // [2L] scale table (two-pass forward)
+  // one-pass step: the two [B, T] int64 modality masks of distillation.py:134-144, written by the same kernel
+  int64_t* lang_mask_out;
+  int64_t* image_mask_out;
 };
 
 // L2 eviction-priority hints (createpolicy); kPolicyNone issues the plain instruction.

@@ -15,22 +15,36 @@ constexpr int kEpiThreads = 1024;
 
 enum EpiFlags { kEpiReduce = 1, kEpiCounts = 2, kEpiLosses = 4, kEpiScale = 8 };
 
-struct EpiParams {
-  const float* ws;        // partial sums (kEpiReduce)
+// What one scalar stage works on (the same record serves the stand-alone kernel and the in-kernel tail).
+struct EpiArgs {
+  const float* ws;        // partial sums (kEpiReduce): [kWsHeaderFloats] header, then [n_part][L][2]
   const int64_t* mask;    // [B, txt] (kEpiCounts)
-  double* sums;           // [2L + 2]: read when a part is not computed here, written when it is
+  double* sums;           // [2L + 2]: read when a part is not computed here, written when it is (may be null)
+  const double* counts_in;  // [2] token counts when kEpiCounts is not set (null: sums + 2L)
   float* out;             // [1 + 3L] (kEpiLosses)
   float* bwd_scale;       // [2L] (kEpiScale)
   long long n_mask;       // B * txt
   double n_vis_rows;      // B * n_vis (or B in cls mode)
+  int n_part;             // number of per-CTA partial blocks in ws (<= 0: read it from the ws header)
   int n_layers;
   int D;
   int loss_kind;
   int flags;
   int comm_first;         // range of the sums vector to allreduce over the peer mailboxes
   int comm_count;         // (0 = no communication)
+  unsigned long long comm_epoch;  // 0: device-side epoch counter; else the host-tracked epoch of the exchange
+};
+
+struct EpiParams {
+  EpiArgs a;
   CommDev comm;
   mafed_weights_t w;
+};
+
+struct EpiSmem {
+  double sums[2 * kMaxLayers + 2];
+  double layer[kMaxLayers];
+  long long cnt[kEpiThreads / 32];
 };
 
 // distillation.py:134-144: language mask = [0 x n_vis | attention_mask], image mask = [1 x n_vis | 0 x txt].
@@ -48,95 +62,91 @@ __global__ void __launch_bounds__(256) k_modality_masks(const int64_t* __restric
   }
 }
 
-__global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant__ EpiParams p) {
-  __shared__ double s_sums[2 * kMaxLayers + 2];
-  __shared__ long long s_cnt[kEpiThreads / 32];
-  __shared__ double s_layer[kMaxLayers];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// The scalar stage itself, run by threads tid = 0..NT-1 of one CTA that synchronise through `sync`.
+template <int NT, typename Sync>
+__device__ __forceinline__ void scalar_stage(const EpiArgs& p, const CommDev& comm, const mafed_weights_t& w,
+                                             EpiSmem& sm, int tid, Sync sync) {
+  const int warp = tid >> 5, lane = tid & 31;
   const int L = p.n_layers;
-  pdl_wait();
-  pdl_launch_dependents();
+  double* s_sums = sm.sums;
 
   if (p.flags & kEpiReduce) {
-    const int n_part = reinterpret_cast<const int*>(p.ws)[0];
+    const int n_part = p.n_part > 0 ? p.n_part : reinterpret_cast<const int*>(p.ws)[0];
     const float* part = p.ws + kWsHeaderFloats;
-    // one warp per (layer, modality) pair; lanes stride over the CTA partials in a fixed order
-    for (int pair = warp; pair < 2 * L; pair += kEpiThreads / 32) {
+    // one warp per (layer, modality) pair; lanes stride over the CTA partials in a fixed order (L2 loads: other
+    // CTAs of the same grid may have written them)
+    for (int pair = warp; pair < 2 * L; pair += NT / 32) {
       double acc = 0.0;
-      for (int b = lane; b < n_part; b += 32) acc += (double)part[(size_t)b * 2 * L + pair];
+      for (int b = lane; b < n_part; b += 32) acc += (double)__ldcg(part + (size_t)b * 2 * L + pair);
       acc = warp_sum(acc);
       if (lane == 0) s_sums[pair] = acc;
     }
   } else if (p.flags & kEpiLosses) {
-    for (int i = threadIdx.x; i < 2 * L; i += kEpiThreads) s_sums[i] = p.sums[i];
+    for (int i = tid; i < 2 * L; i += NT) s_sums[i] = p.sums[i];
   }
   if (p.flags & kEpiCounts) {
     // text-token count = sum of the attention mask (distillation.py:248 `mask.sum()`)
     long long c = 0;
-    for (long long i = threadIdx.x; i < p.n_mask; i += kEpiThreads) c += p.mask[i];
+    for (long long i = tid; i < p.n_mask; i += NT) c += p.mask[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) s_cnt[warp] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (lane == 0) sm.cnt[warp] = c;
+    sync();
+    if (tid == 0) {
       long long tot = 0;
-      for (int i = 0; i < kEpiThreads / 32; ++i) tot += s_cnt[i];
+      for (int i = 0; i < NT / 32; ++i) tot += sm.cnt[i];
       s_sums[2 * L] = (double)tot;
       s_sums[2 * L + 1] = p.n_vis_rows;
     }
-  } else if (threadIdx.x < 2) {
-    s_sums[2 * L + threadIdx.x] = p.sums[2 * L + threadIdx.x];
+  } else if (tid < 2) {
+    const double* src = p.counts_in != nullptr ? p.counts_in : p.sums + 2 * L;
+    s_sums[2 * L + tid] = src[tid];
   }
-  __syncthreads();
+  sync();
   // batch-sharded step: combine this rank's sums / counts with its peers' over NVLink, in this kernel
-  if (p.comm.world > 1 && p.comm_count > 0) peer_allreduce(p.comm, s_sums + p.comm_first, p.comm_count);
+  if (comm.world > 1 && p.comm_count > 0)
+    peer_allreduce<NT>(comm, s_sums + p.comm_first, p.comm_count, tid, sync, p.comm_epoch);
   if (p.sums != nullptr) {
     if (p.flags & kEpiReduce)
-      for (int i = threadIdx.x; i < 2 * L; i += kEpiThreads) p.sums[i] = s_sums[i];
-    if ((p.flags & kEpiCounts) && threadIdx.x < 2) p.sums[2 * L + threadIdx.x] = s_sums[2 * L + threadIdx.x];
+      for (int i = tid; i < 2 * L; i += NT) p.sums[i] = s_sums[i];
+    if (((p.flags & kEpiCounts) || p.counts_in != nullptr) && tid < 2) p.sums[2 * L + tid] = s_sums[2 * L + tid];
   }
   if (!(p.flags & (kEpiLosses | kEpiScale))) return;
 
   const bool want_loss = p.flags & kEpiLosses, want_scale = p.flags & kEpiScale;
   const double n_text = s_sums[2 * L], n_vis = s_sums[2 * L + 1];
   const double k = (p.loss_kind == MAFED_LOSS_MSE) ? 1.0 / (double)p.D : 1.0;
-  const bool cls = p.w.modality_kind == MAFED_MODW_CLS;
-  const bool text_only = p.w.modality_kind == MAFED_MODW_TEXT_ONLY;
-  for (int l = threadIdx.x; l < L; l += kEpiThreads) {
+  const bool cls = w.modality_kind == MAFED_MODW_CLS;
+  const bool text_only = w.modality_kind == MAFED_MODW_TEXT_ONLY;
+  for (int l = tid; l < L; l += NT) {
     double wt, wv;
-    if (p.w.modality_kind == MAFED_MODW_EQUAL) {
-      wt = (double)(float)(n_text / (n_text + n_vis));
-      wv = (double)(float)(n_vis / (n_text + n_vis));
-    } else if (p.w.modality_kind == MAFED_MODW_TABLE) {
-      wt = (double)p.w.lang_weight[l];
-      wv = (double)(float)(1.0 - wt);
-    } else if (text_only) {
-      wt = 1.0;
-      wv = 0.0;
-    } else {  // CLS: vision slot only
-      wt = 0.0;
-      wv = 1.0;
-    }
-    const double c = (double)p.w.layer_coeff[l] * (double)p.w.distill_coeff;
+    modality_weights(w, l, n_text, n_vis, wt, wv);
+    const double c = (double)w.layer_coeff[l] * (double)w.distill_coeff;
     if (want_loss) {
       const double text_loss = cls ? 0.0 : s_sums[2 * l] * k / n_text;  // 0/0 -> NaN, as in the reference
       const double vis_loss = text_only ? 0.0 : s_sums[2 * l + 1] * k / n_vis;
       const double layer_loss = cls ? vis_loss : (text_only ? text_loss : wt * text_loss + wv * vis_loss);
-      s_layer[l] = c * layer_loss;
+      sm.layer[l] = c * layer_loss;
       p.out[1 + l] = (float)layer_loss;
       p.out[1 + L + 2 * l] = (float)text_loss;
       p.out[1 + L + 2 * l + 1] = (float)vis_loss;
     }
-    if (want_scale)
-      backward_scales(p.w, l, n_text, n_vis, p.loss_kind, p.D, p.bwd_scale[2 * l], p.bwd_scale[2 * l + 1]);
+    if (want_scale) backward_scales(w, l, n_text, n_vis, p.loss_kind, p.D, p.bwd_scale[2 * l], p.bwd_scale[2 * l + 1]);
   }
   if (!want_loss) return;
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  sync();
+  if (tid == 0) {
     double tot = 0.0;
-    for (int l = 0; l < L; ++l) tot += s_layer[l];
+    for (int l = 0; l < L; ++l) tot += sm.layer[l];
     p.out[0] = (float)tot;
   }
+}
+
+__global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant__ EpiParams p) {
+  __shared__ EpiSmem sm;
+  pdl_wait();
+  pdl_launch_dependents();
+  scalar_stage<kEpiThreads>(p.a, p.comm, p.w, sm, (int)threadIdx.x, SyncCta());
 }
 
 }  // namespace mafed

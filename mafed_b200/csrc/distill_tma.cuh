@@ -5,6 +5,7 @@
 #pragma once
 #include "distill_comm.cuh"
 #include "distill_common.cuh"
+#include "distill_epilogue.cuh"
 
 namespace mafed {
 
@@ -145,6 +146,43 @@ __device__ __forceinline__ void tma_prologue(TmaSmem& sm, const TmaGeom& geo) {
   pdl_wait();
 }
 
+// ---------------------------------------------------------------- in-kernel tail
+// Called by the NT consumer threads of every CTA after its partial sums are in `ws`: the CTA that arrives
+// last at the counter reduces all partials in fixed order and runs the scalar stage (losses, scale table,
+// peer exchange) -- what a separate single-CTA epilogue launch would do.  The order of the reduction does
+// not depend on which CTA is last, so results stay bit-reproducible.
+template <int NT>
+__device__ __forceinline__ void tma_tail(const PathParams& p, const double* counts_in) {
+  __shared__ int s_last;
+  __shared__ EpiSmem s_epi;
+  __threadfence();  // this thread's partial-sum stores are visible device-wide before the arrival below
+  named_bar_sync(1, NT);
+  if (threadIdx.x == 0) s_last = atomicAdd(p.tail_done, 1u) == gridDim.x - 1u;
+  named_bar_sync(1, NT);
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *p.tail_done = 0u;  // every other CTA has arrived: leave the counter clean for its next user
+  EpiArgs a;
+  a.ws = p.ws;
+  a.mask = p.mask;
+  a.sums = p.tail_sums;
+  a.counts_in = counts_in;
+  a.out = p.tail_out;
+  a.bwd_scale = p.tail_bwd_scale;
+  a.n_mask = p.n_mask;
+  a.n_vis_rows = p.n_vis_rows;
+  a.n_part = (int)gridDim.x;
+  a.n_layers = p.n_layers;
+  a.D = p.D;
+  a.loss_kind = p.loss_kind;
+  a.flags = p.tail_flags;
+  a.comm_first = 0;
+  a.comm_count = p.tail_comm ? (2 * p.n_layers + ((p.tail_flags & kEpiCounts) ? 2 : 0)) : 0;
+  // after an in-kernel counts exchange (host-tracked epoch) the sums exchange is the next epoch
+  a.comm_epoch = (counts_in != nullptr && p.comm.world > 1) ? p.comm_epoch + 1ull : 0ull;
+  scalar_stage<NT>(a, p.comm, p.w, s_epi, (int)threadIdx.x, SyncNamed<NT>());
+}
+
 // ---------------------------------------------------------------- forward
 template <typename T, int LOSS, int NCW>
 __global__ void __launch_bounds__((NCW + 1) * 32, 1)
@@ -226,6 +264,7 @@ k_fwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
   cta_sums_flush(sums, warp, lane, cur, acc_text, acc_vis);
   named_bar_sync(1, NCW * 32);
   cta_sums_store(sums, p.ws, p.n_layers, 0, NCW * 32);
+  if (p.tail_flags) tma_tail<NCW * 32>(p, nullptr);
 }
 
 // ---------------------------------------------------------------- backward
@@ -268,6 +307,18 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
   // tiles are in flight, the consumer warps count the valid text tokens themselves (the mask is a few KB,
   // L2-resident) and derive the table; CTA 0 publishes it for the later backward fix-up.
   __shared__ float s_scale[2 * kMaxLayers];
+  __shared__ double s_counts[2];  // (global) token counts, kept for the tail
+  if (FUSED && p.lang_mask_out != nullptr) {
+    // the masks the reference leaves in `batch` (distillation.py:134-144): a few hundred KB spread over all CTAs
+    const long long n = p.n_rows;
+    for (long long i = (long long)blockIdx.x * (NCW * 32) + threadIdx.x; i < n; i += (long long)gridDim.x * (NCW * 32)) {
+      const long long b = i / p.T;
+      const int t = (int)(i - b * p.T);
+      const bool vis = t < p.n_vis;
+      p.lang_mask_out[i] = vis ? 0 : p.mask[b * p.txt + (t - p.n_vis)];
+      p.image_mask_out[i] = vis ? 1 : 0;
+    }
+  }
   if (FUSED && p.inline_scale) {
     __shared__ long long s_cnt[NCW];
     long long c = 0;
@@ -313,6 +364,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
         n_vis_rows += __ldcg(mine + (size_t)r * kCommSlots + 1);
       }
     }
+    if (threadIdx.x == 0) { s_counts[0] = n_text; s_counts[1] = n_vis_rows; }
     if ((int)threadIdx.x < p.n_layers) {
       float st, sv;
       backward_scales(p.w, threadIdx.x, n_text, n_vis_rows, p.loss_kind, p.D, st, sv);
@@ -472,6 +524,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
     cta_sums_flush(sums, warp, lane, cur, acc_text, acc_vis);
     named_bar_sync(1, NCW * 32);
     cta_sums_store(sums, p.ws, p.n_layers, 0, NCW * 32);
+    if (p.tail_flags) tma_tail<NCW * 32>(p, s_counts);
   }
 }
 

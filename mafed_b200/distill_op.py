@@ -2,13 +2,15 @@
 
 Two ways to run a step, same results:
 
-* two-pass  -- fused forward over all selected layers (+ a single-CTA epilogue), later one fused
-  backward: 5*D*e bytes of HBM traffic per token*layer;
+* two-pass  -- fused forward over all selected layers (the loss algebra runs in the kernel's last CTA),
+  later one fused backward: 5*D*e bytes of HBM traffic per token*layer, two launches;
 * one-pass  -- the gradient scale depends only on the token counts and the host weight tables, not
   on the loss, so one kernel produces the loss sums AND the gradients from a single read of student
   and teacher (3*D*e bytes).  The upstream gradient is assumed (``plan.assumed_grad_out``, i.e.
   ``1 / accumulate_grad_batches`` under Lightning); ``backward`` launches a fix-up that returns at
   once when the real upstream gradient equals the assumed one and otherwise recomputes exactly.
+  The whole step -- modality masks, scale table, loss sums, gradients, losses, and across batch
+  shards the NVLink exchange of counts and sums -- is ONE kernel launch (``mafed_distill_step``).
 
 Under ``torch.distributed`` with batch sharding, the per-rank ``[2L+2]`` fp64 partial sums / counts
 are combined by allreduce; the backward needs no collective.  Nothing here
@@ -181,6 +183,17 @@ def modality_masks(attn_mask: torch.Tensor, n_vis: int):
     return lang, image
 
 
+def modality_masks_into(attn_mask: torch.Tensor, n_vis: int, lang: torch.Tensor, image: torch.Tensor):
+    """``modality_masks`` into pre-allocated int64 ``[B, n_vis + txt]`` outputs (``attn_mask`` int64, contiguous)."""
+    lib = cabi.load()
+    B, txt = attn_mask.shape
+    shape = cabi.make_shape(1, B, n_vis + txt, n_vis, 1, cabi.F32, cabi.LOSS_MSE)
+    with _on_device(attn_mask.device):
+        cabi.check(lib.mafed_distill_modality_masks(ctypes.byref(shape), attn_mask.data_ptr(), lang.data_ptr(),
+                                                    image.data_ptr(), _stream_ptr(attn_mask.device)),
+                   "mafed_distill_modality_masks")
+
+
 def token_norm_sums(tensors: Sequence[torch.Tensor], attn_mask: torch.Tensor, n_vis: int) -> torch.Tensor:
     """Masked per-modality sums of the per-token L2 norms of ``len(tensors)`` ``[B, T, D]`` tensors in one
     fused pass (``distillation_loss_weights.py:122-137``).  Returns device fp64 ``[2L + 2]``:
@@ -220,7 +233,8 @@ def allreduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def distill_forward(students, teachers, attn_mask, plan: DistillPlan, group=None):
-    """Two-pass step, first half: fused forward + epilogue.  Returns ``(out, bwd_scale, launch)``.
+    """Two-pass step, first half: the fused forward; its last CTA reduces the partial sums and forms the
+    losses and the backward scale table (one launch).  Returns ``(out, bwd_scale, launch)``.
 
     ``out`` is a device fp32 vector ``[1 + 3L]``: total loss, L layer losses (what the reference
     logs to W&B, ``distillation.py:165``), then L x (text loss, vision loss).
@@ -231,19 +245,12 @@ def distill_forward(students, teachers, attn_mask, plan: DistillPlan, group=None
     with _on_device(dev):
         stream = _stream_ptr(dev)
         ws, out, bwd_scale = ln.alloc_scalars(lib)
-        cabi.check(lib.mafed_distill_fwd(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, ln.mask_ptr, ws.data_ptr(), stream),
-                   "mafed_distill_fwd")
         w = ctypes.byref(plan.weights())
         distributed, pg = resolve_group(group)
         peer = get_peer_comm(pg) if distributed else None
-        if peer is not None:
-            # reduce + counts + NVLink peer allreduce + losses + scale: one launch, no NCCL call
-            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
-            every = cabi.STAGE_REDUCE | cabi.STAGE_COUNTS | cabi.STAGE_LOSSES | cabi.STAGE_SCALE
-            cabi.check(lib.mafed_distill_scalar_stage_comm(
-                ln.shape_ref, w, every, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), out.data_ptr(),
-                bwd_scale.data_ptr(), peer.handle, cabi.COMM_SUMS | cabi.COMM_COUNTS, stream), "scalar_stage_comm")
-        elif distributed:
+        if distributed and peer is None:
+            cabi.check(lib.mafed_distill_fwd(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, ln.mask_ptr, ws.data_ptr(), stream),
+                       "mafed_distill_fwd")
             sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
             cabi.check(lib.mafed_distill_reduce(ln.shape_ref, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream),
                        "mafed_distill_reduce")
@@ -251,8 +258,12 @@ def distill_forward(students, teachers, attn_mask, plan: DistillPlan, group=None
             cabi.check(lib.mafed_distill_finalize(ln.shape_ref, w, sums.data_ptr(), out.data_ptr(),
                                                   bwd_scale.data_ptr(), stream), "mafed_distill_finalize")
         else:
-            cabi.check(lib.mafed_distill_epilogue(ln.shape_ref, w, ln.mask_ptr, ws.data_ptr(), None, out.data_ptr(),
-                                                  bwd_scale.data_ptr(), stream), "mafed_distill_epilogue")
+            # forward + reduce + counts (+ NVLink peer allreduce) + losses + scale: one launch, no NCCL call
+            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev) if peer is not None else None
+            cabi.check(lib.mafed_distill_fwd_step(
+                ln.shape_ref, ln.s_ptrs, ln.t_ptrs, ln.mask_ptr, w, ws.data_ptr(), out.data_ptr(),
+                bwd_scale.data_ptr(), sums.data_ptr() if sums is not None else None,
+                peer.handle if peer is not None else None, stream), "mafed_distill_fwd_step")
     return out, bwd_scale, ln
 
 
@@ -270,9 +281,10 @@ def distill_backward(ln: _Launch, grads: Sequence[Optional[torch.Tensor]], bwd_s
                                          skip, _stream_ptr(ln.device)), "mafed_distill_bwd")
 
 
-def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group=None):
-    """One-pass step: prologue (counts -> gradient scale), the fused kernel (loss sums + gradients from
-    one read of student and teacher), epilogue (losses).  Returns ``(out, bwd_scale, launch)``."""
+def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group=None, mask_out=None):
+    """One-pass step: counts -> gradient scale, loss sums + gradients from one read of student and teacher,
+    losses -- a single launch of the fused kernel (``mafed_distill_step``); ``mask_out = (lang, image)`` int64
+    ``[B, T]`` tensors are filled by the same kernel.  Returns ``(out, bwd_scale, launch)``."""
     lib = cabi.load()
     ln = _Launch(students, teachers, attn_mask, plan)
     L, dev = ln.n_layers, ln.device
@@ -284,19 +296,22 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
         w = ctypes.byref(plan.weights())
         distributed, pg = resolve_group(group)
         peer = get_peer_comm(pg) if distributed else None
-        if peer is not None:
-            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
-            if not torch.cuda.is_current_stream_capturing():
-                # two launches, as on one GPU: the counts are exchanged inside the fused kernel (hidden behind its
-                # first tiles), sums + counts inside the epilogue
-                cabi.check(lib.mafed_distill_fused_comm(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr, w,
-                                                        bwd_scale.data_ptr(), fixed, ws.data_ptr(), peer.handle,
-                                                        stream), "mafed_distill_fused_comm")
-                cabi.check(lib.mafed_distill_scalar_stage_comm(
-                    ln.shape_ref, w, cabi.STAGE_REDUCE | cabi.STAGE_COUNTS | cabi.STAGE_LOSSES, ln.mask_ptr,
-                    ws.data_ptr(), sums.data_ptr(), out.data_ptr(), None, peer.handle,
-                    cabi.COMM_SUMS | cabi.COMM_COUNTS, stream), "epilogue_comm")
-                return out, bwd_scale, ln
+        capturing = peer is not None and torch.cuda.is_current_stream_capturing()
+        if not distributed or (peer is not None and not capturing):
+            # one launch, on one GPU and across batch shards alike: with a communicator the counts are exchanged
+            # inside the kernel behind its first tiles and the sums by its last CTA (NVLink peer stores, no NCCL)
+            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev) if peer is not None else None
+            lang, image = mask_out if mask_out is not None else (None, None)
+            cabi.check(lib.mafed_distill_step(
+                ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr, w, fixed, ws.data_ptr(), out.data_ptr(),
+                bwd_scale.data_ptr(), sums.data_ptr() if sums is not None else None,
+                lang.data_ptr() if lang is not None else None, image.data_ptr() if image is not None else None,
+                peer.handle if peer is not None else None, stream), "mafed_distill_step")
+            return out, bwd_scale, ln
+        if mask_out is not None:
+            modality_masks_into(ln.mask, plan.n_vis, *mask_out)
+        sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
+        if capturing:
             # under CUDA-graph capture: device-side epochs only (prologue with the counts exchange)
             cabi.check(lib.mafed_distill_scalar_stage_comm(
                 ln.shape_ref, w, cabi.STAGE_COUNTS | cabi.STAGE_SCALE, ln.mask_ptr, None, sums.data_ptr(), None,
@@ -308,26 +323,19 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
                 ln.shape_ref, w, cabi.STAGE_REDUCE | cabi.STAGE_LOSSES, None, ws.data_ptr(), sums.data_ptr(),
                 out.data_ptr(), None, peer.handle, cabi.COMM_SUMS, stream), "epilogue_comm")
             return out, bwd_scale, ln
-        if distributed:
-            sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
-            cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_COUNTS, ln.mask_ptr, None,
-                                                      sums.data_ptr(), None, None, stream), "counts")
-            allreduce_sums(sums[2 * L:], pg)
-            cabi.check(lib.mafed_distill_prologue(ln.shape_ref, w, None, sums.data_ptr(), None, bwd_scale.data_ptr(),
-                                                  stream), "mafed_distill_prologue")
-        # single rank: passing the weights makes the kernel derive the scale table itself (no prologue launch)
-        cabi.check(lib.mafed_distill_fused(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr,
-                                           None if distributed else w, bwd_scale.data_ptr(), fixed, ws.data_ptr(),
-                                           stream), "mafed_distill_fused")
-        if distributed:
-            cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_REDUCE, None, ws.data_ptr(),
-                                                      sums.data_ptr(), None, None, stream), "reduce")
-            allreduce_sums(sums[: 2 * L], pg)
-            cabi.check(lib.mafed_distill_finalize(ln.shape_ref, w, sums.data_ptr(), out.data_ptr(), None, stream),
-                       "mafed_distill_finalize")
-        else:
-            cabi.check(lib.mafed_distill_epilogue(ln.shape_ref, w, ln.mask_ptr, ws.data_ptr(), None, out.data_ptr(),
-                                                  None, stream), "mafed_distill_epilogue")
+        # NCCL: counts allreduce -> scale table -> fused pass -> sums allreduce -> losses
+        cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_COUNTS, ln.mask_ptr, None,
+                                                  sums.data_ptr(), None, None, stream), "counts")
+        allreduce_sums(sums[2 * L:], pg)
+        cabi.check(lib.mafed_distill_prologue(ln.shape_ref, w, None, sums.data_ptr(), None, bwd_scale.data_ptr(),
+                                              stream), "mafed_distill_prologue")
+        cabi.check(lib.mafed_distill_fused(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr, None,
+                                           bwd_scale.data_ptr(), fixed, ws.data_ptr(), stream), "mafed_distill_fused")
+        cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_REDUCE, None, ws.data_ptr(),
+                                                  sums.data_ptr(), None, None, stream), "reduce")
+        allreduce_sums(sums[: 2 * L], pg)
+        cabi.check(lib.mafed_distill_finalize(ln.shape_ref, w, sums.data_ptr(), out.data_ptr(), None, stream),
+                   "mafed_distill_finalize")
     return out, bwd_scale, ln
 
 
@@ -348,20 +356,23 @@ def _alloc_grads(students, needs: Sequence[bool], cls: bool):
 
 
 class _DistillFunction(torch.autograd.Function):
-    """Inputs: (plan, attention_mask, group, teachers tuple, *students).  The teachers ride in a plain tuple:
-    they never need gradients, so autograd does not have to look at them."""
+    """Inputs: (plan, attention_mask, group, teachers tuple, mask_out, *students).  The teachers ride in a plain
+    tuple: they never need gradients, so autograd does not have to look at them.  ``mask_out``: ``None`` or the
+    pre-allocated ``(lang_masks, image_masks)`` pair to fill (``distillation.py:134-144``)."""
 
     @staticmethod
-    def forward(ctx, plan: DistillPlan, attn_mask, group, teachers, *students):
+    def forward(ctx, plan: DistillPlan, attn_mask, group, teachers, mask_out, *students):
         students = _prepare(students)
-        needs = ctx.needs_input_grad[4:]
+        needs = ctx.needs_input_grad[5:]
         ctx.plan, ctx.needs, ctx.grads = plan, needs, None
         if plan.single_pass and any(needs):
             grads = _alloc_grads(students, needs, plan.cls)
-            out, bwd_scale, ln = distill_fused(students, teachers, grads, attn_mask, plan, group)
+            out, bwd_scale, ln = distill_fused(students, teachers, grads, attn_mask, plan, group, mask_out)
             ctx.grads = grads
         else:
             out, bwd_scale, ln = distill_forward(students, teachers, attn_mask, plan, group)
+            if mask_out is not None:
+                modality_masks_into(ln.mask, plan.n_vis, *mask_out)
         ctx.launch, ctx.bwd_scale = ln, bwd_scale
         # registered with autograd so that an in-place modification of a hidden state between forward and
         # backward is detected (the backward / fix-up kernel would otherwise read the modified values)
@@ -375,7 +386,7 @@ class _DistillFunction(torch.autograd.Function):
     def backward(ctx, grad_total, _grad_aux):
         ln, plan = ctx.launch, ctx.plan
         if grad_total is None or ln is None or not any(ctx.needs):
-            return (None,) * (4 + len(ctx.needs))
+            return (None,) * (5 + len(ctx.needs))
         _ = ctx.saved_tensors   # version-counter check of students / teachers
         g = grad_total
         if g.dtype != torch.float32 or g.device != ln.device:
@@ -392,15 +403,17 @@ class _DistillFunction(torch.autograd.Function):
         else:
             grads = _alloc_grads(ln.students, ctx.needs, plan.cls)
             distill_backward(ln, grads, ctx.bwd_scale, g)
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor], attn_mask, plan: DistillPlan,
-                 group=None, teachers_detached: bool = False):
+                 group=None, teachers_detached: bool = False, mask_out=None):
     """Differentiable fused distillation loss over ``len(students)`` selected layers.
 
     Returns ``(total, aux)``: ``total`` is the 0-dim fp32 loss (gradients flow to ``students``),
     ``aux`` the non-differentiable ``[3L]`` vector of layer losses then (text, vision) losses.
+    ``mask_out``: optional pre-allocated int64 ``(lang_masks, image_masks)`` ``[B, T]`` pair, filled by the
+    step's own kernel (``attn_mask`` must then be a contiguous int64 CUDA tensor).
     """
     students = list(students)
     teachers = list(teachers) if teachers_detached else [t.detach() for t in teachers]
@@ -423,7 +436,7 @@ def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tens
     teachers = _prepare(teachers)
     n = len(students)
     if n <= cabi.MAX_LAYERS:
-        return _DistillFunction.apply(plan, attn_mask, group, tuple(teachers), *students)
+        return _DistillFunction.apply(plan, attn_mask, group, tuple(teachers), mask_out, *students)
     # more selected layers than one launch carries (MAFED_MAX_LAYERS): chunk and add the partial totals
     total, layer_losses, modal_losses = None, [], []
     for lo in range(0, n, cabi.MAX_LAYERS):
@@ -434,7 +447,8 @@ def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tens
                           loss_kind=plan.loss_kind, cls=plan.cls, n_vis=plan.n_vis,
                           grad_multiplier=plan.grad_multiplier, single_pass=plan.single_pass,
                           assumed_grad_out=plan.assumed_grad_out)
-        part, aux = _DistillFunction.apply(sub, attn_mask, group, tuple(teachers[lo:hi]), *students[lo:hi])
+        part, aux = _DistillFunction.apply(sub, attn_mask, group, tuple(teachers[lo:hi]), mask_out if lo == 0 else None,
+                                           *students[lo:hi])
         total = part if total is None else total + part
         layer_losses.append(aux[: hi - lo])
         modal_losses.append(aux[hi - lo:])

@@ -238,13 +238,19 @@ class FeatureDistillation(CLStrategy):
                            single_pass=self.single_pass, assumed_grad_out=self.assumed_grad_out)
 
     def _launch(self, plan: DistillPlan, batch, students, teachers, teachers_detached=False):
-        attn = None
+        attn, mask_out = None, None
         if not plan.cls:
             attn = batch["attention_mask"]
             if self.populate_batch_masks:
-                batch["lang_masks"], batch["image_masks"] = modality_masks(attn, self.num_vision_tokens)
+                if attn.is_cuda and attn.dtype == torch.int64 and attn.is_contiguous():
+                    # the masks the reference leaves in `batch` are written by the step's own kernel
+                    both = torch.empty((2, attn.shape[0], self.num_vision_tokens + attn.shape[1]),
+                                       dtype=torch.int64, device=attn.device)
+                    batch["lang_masks"], batch["image_masks"] = mask_out = (both[0], both[1])
+                else:
+                    batch["lang_masks"], batch["image_masks"] = modality_masks(attn, self.num_vision_tokens)
         return distill_loss(students, teachers, attn, plan, group=self.process_group,
-                            teachers_detached=teachers_detached)
+                            teachers_detached=teachers_detached, mask_out=mask_out)
 
     def _get_past_hidden_states(self, batch):
         with torch.no_grad():
