@@ -369,7 +369,7 @@ CommDev comm_dev(const mafed_comm* c) {
 
 int launch_scalar_stage(const mafed_shape_t& sh, const mafed_weights_t* w, int flags, const int64_t* mask,
                         const void* ws, double* sums, float* out, float* bwd_scale, cudaStream_t st,
-                        const mafed_comm* comm = nullptr, int comm_what = 0) {
+                        const mafed_comm* comm = nullptr, int comm_what = 0, double* counts_out = nullptr) {
   EpiParams e;
   memset(&e, 0, sizeof(e));
   e.comm = comm_dev(comm);
@@ -383,6 +383,7 @@ int launch_scalar_stage(const mafed_shape_t& sh, const mafed_weights_t* w, int f
   e.a.ws = reinterpret_cast<const float*>(ws);
   e.a.mask = mask;
   e.a.sums = sums;
+  e.a.counts_out = counts_out;
   e.a.out = out;
   e.a.bwd_scale = bwd_scale;
   e.a.n_mask = mask_entries(sh);
@@ -416,44 +417,53 @@ int fused_impl(const mafed_shape_t* shape, const void* const* student_ptrs, cons
   p.bwd_scale = bwd_scale;
   p.fixed_gout = assumed_grad_out;
   p.ws = reinterpret_cast<float*>(ws);
+  const bool sharded = comm != nullptr && comm->world > 1;
+  const bool tma = uses_tma(*shape, p, kPassFused);
+  // With `tail` the last CTA of the TMA kernel reduces the partials and forms the losses (and exchanges the sums
+  // with the peers), and all CTAs write the modality masks: no epilogue or mask launch.
+  unsigned int* done = nullptr;
+  if (tail != nullptr && weights != nullptr && tma && !g_tune[kTuneNoTail].load()) done = next_tail_counter();
+  if (done != nullptr) {
+    p.tail_flags = kEpiReduce | kEpiLosses;
+    p.tail_done = done;
+    p.tail_out = tail->out;
+    p.tail_sums = tail->sums;
+    p.lang_mask_out = tail->lang_mask;
+    p.image_mask_out = tail->image_mask;
+    p.loss_kind = shape->loss_kind;
+    p.n_mask = mask_entries(*shape);
+    p.n_vis_rows = vis_rows(*shape);
+    p.w = *weights;
+    if (sharded) {
+      p.comm = comm_dev(comm);
+      p.tail_comm = 1;
+    }
+    if (folded != nullptr) *folded = true;
+  }
   if (weights != nullptr) {
-    // single-rank step: the scale table is this call's business.  Small masks: every CTA of the TMA kernel
-    // derives it itself while its first tiles are in flight; otherwise one prologue launch.
+    // the scale table is this call's business.  Small masks: every CTA of the TMA kernel derives it itself while
+    // its first tiles are in flight (the whole step is ONE launch); otherwise one prologue launch, which leaves the
+    // counts in the ws header for the tail.
     const long long n_mask = mask_entries(*shape);
-    if (n_mask <= 16384 && !g_tune[kTuneNoInlineScale].load() && uses_tma(*shape, p, kPassFused)) {
+    if (n_mask <= 16384 && !g_tune[kTuneNoInlineScale].load() && tma) {
       p.inline_scale = 1;
       p.loss_kind = shape->loss_kind;
       p.n_mask = n_mask;
       p.n_vis_rows = vis_rows(*shape);
       p.bwd_scale_out = bwd_scale;
       p.w = *weights;
-      const bool sharded = comm != nullptr && comm->world > 1;
-      if (sharded) {   // the counts exchange rides inside the kernel
+      if (sharded) {   // the counts exchange rides inside the kernel, on host-tracked epochs
         p.comm = comm_dev(comm);
         p.comm_epoch = ++comm->host_epoch;
       }
-      unsigned int* done = nullptr;
-      if (tail != nullptr && !g_tune[kTuneNoTail].load()) done = next_tail_counter();
-      if (done != nullptr) {
-        // the last CTA to finish reduces the partials and forms the losses (and exchanges the sums with the peers):
-        // the whole step is this one launch
-        p.tail_flags = kEpiReduce | kEpiLosses;
-        p.tail_done = done;
-        p.tail_out = tail->out;
-        p.tail_sums = tail->sums;
-        p.lang_mask_out = tail->lang_mask;
-        p.image_mask_out = tail->image_mask;
-        if (sharded) {
-          p.tail_comm = 1;
-          ++comm->host_epoch;   // the sums exchange is epoch comm_epoch + 1
-        }
-        if (folded != nullptr) *folded = true;
-      }
     } else {
+      double* counts = reinterpret_cast<double*>(p.ws + kWsCountsAt);
+      p.tail_counts_in = counts;
       rc = launch_scalar_stage(*shape, weights, MAFED_STAGE_COUNTS | MAFED_STAGE_SCALE, attn_mask, nullptr, nullptr,
-                               nullptr, bwd_scale, (cudaStream_t)stream, comm, MAFED_COMM_COUNTS);
+                               nullptr, bwd_scale, (cudaStream_t)stream, comm, MAFED_COMM_COUNTS, counts);
       if (rc) return rc;
     }
+    if (done != nullptr && sharded) ++comm->host_epoch;   // the tail's sums exchange
   }
   return dispatch(*shape, p, kPassFused, (cudaStream_t)stream);
 }

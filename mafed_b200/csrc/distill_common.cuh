@@ -15,7 +15,10 @@ constexpr int kMaxLayers = MAFED_MAX_LAYERS;
 constexpr int kLossL2Norm = 2;
 constexpr float kCosEps = 1e-12f;  // EPSILON of ATen's cosine_embedding_loss
 constexpr int kMaxPartials = 2048;  // upper bound on CTAs writing partial sums
-constexpr int kWsHeaderFloats = 4;  // ws[0] = number of partial blocks (as int)
+// ws header: [0] = number of partial blocks (int); [2..5] = two doubles, the (global) token counts a prologue
+// launch leaves for the in-kernel tail of the streaming kernel that follows it
+constexpr int kWsHeaderFloats = 8;
+constexpr int kWsCountsAt = 2;
 
 // Peer-memory communicator as the kernels see it (see distill_comm.cuh).
 constexpr int kCommMaxRanks = 16;
@@ -67,6 +70,7 @@ struct PathParams {
   // In-kernel tail (TMA kernels): the last CTA to finish runs the scalar stage on the partial sums, so the step
   // needs no epilogue launch.  Needs w / loss_kind / n_mask / n_vis_rows above (and comm for a sharded step).
   int tail_flags;                // 0: no tail; else EpiFlags of the stage to run
+  const double* tail_counts_in;  // [2] counts from a prologue launch (fused pass without the in-kernel scale table)
   int tail_comm;                 // 1: allreduce the sums (+ counts when computed in the tail) over the peer mailboxes
   unsigned int* tail_done;       // arrival counter: zero on entry, reset by the last CTA
   double* tail_sums;             // optional [2L + 2] copy of the (global) sums and counts

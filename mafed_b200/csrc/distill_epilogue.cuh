@@ -20,6 +20,7 @@ struct EpiArgs {
   const float* ws;        // partial sums (kEpiReduce): [kWsHeaderFloats] header, then [n_part][L][2]
   const int64_t* mask;    // [B, txt] (kEpiCounts)
   double* sums;           // [2L + 2]: read when a part is not computed here, written when it is (may be null)
+  double* counts_out;     // optional second copy of the two (global) counts (the ws header, for a later tail)
   const double* counts_in;  // [2] token counts when kEpiCounts is not set (null: sums + 2L)
   float* out;             // [1 + 3L] (kEpiLosses)
   float* bwd_scale;       // [2L] (kEpiScale)
@@ -111,6 +112,7 @@ __device__ __forceinline__ void scalar_stage(const EpiArgs& p, const CommDev& co
       for (int i = tid; i < 2 * L; i += NT) p.sums[i] = s_sums[i];
     if (((p.flags & kEpiCounts) || p.counts_in != nullptr) && tid < 2) p.sums[2 * L + tid] = s_sums[2 * L + tid];
   }
+  if (p.counts_out != nullptr && tid < 2) p.counts_out[tid] = s_sums[2 * L + tid];
   if (!(p.flags & (kEpiLosses | kEpiScale))) return;
 
   const bool want_loss = p.flags & kEpiLosses, want_scale = p.flags & kEpiScale;

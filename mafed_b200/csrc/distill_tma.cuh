@@ -166,6 +166,7 @@ __device__ __forceinline__ void tma_tail(const PathParams& p, const double* coun
   a.ws = p.ws;
   a.mask = p.mask;
   a.sums = p.tail_sums;
+  a.counts_out = nullptr;
   a.counts_in = counts_in;
   a.out = p.tail_out;
   a.bwd_scale = p.tail_bwd_scale;
@@ -178,8 +179,9 @@ __device__ __forceinline__ void tma_tail(const PathParams& p, const double* coun
   a.flags = p.tail_flags;
   a.comm_first = 0;
   a.comm_count = p.tail_comm ? (2 * p.n_layers + ((p.tail_flags & kEpiCounts) ? 2 : 0)) : 0;
-  // after an in-kernel counts exchange (host-tracked epoch) the sums exchange is the next epoch
-  a.comm_epoch = (counts_in != nullptr && p.comm.world > 1) ? p.comm_epoch + 1ull : 0ull;
+  // after an in-kernel counts exchange (host-tracked epoch) the sums exchange is the next epoch; otherwise the
+  // device-side epoch counter is used
+  a.comm_epoch = p.comm_epoch != 0ull ? p.comm_epoch + 1ull : 0ull;
   scalar_stage<NT>(a, p.comm, p.w, s_epi, (int)threadIdx.x, SyncNamed<NT>());
 }
 
@@ -524,7 +526,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
     cta_sums_flush(sums, warp, lane, cur, acc_text, acc_vis);
     named_bar_sync(1, NCW * 32);
     cta_sums_store(sums, p.ws, p.n_layers, 0, NCW * 32);
-    if (p.tail_flags) tma_tail<NCW * 32>(p, s_counts);
+    if (p.tail_flags) tma_tail<NCW * 32>(p, p.inline_scale ? s_counts : p.tail_counts_in);
   }
 }
 

@@ -100,6 +100,35 @@ def test_forward_step_equals_forward_plus_epilogue(dtype):
         assert rel_err(gl.float().cpu(), ref["grads"][l].float()) < tol
 
 
+def test_large_mask_step_keeps_the_tail():
+    """More than 16 Ki mask entries: the counts come from a prologue launch (left in the ws header), the loss
+    algebra and the masks still run inside the fused kernel."""
+    L, B, txt, D = 2, 70, 256, 256
+    st, te, am = O.make_inputs(L + 1, B, txt, D, n_vis=256, dtype=torch.bfloat16, seed=13)
+    cfg, plan = _plan(L, "mse", "equal")
+    s = [st[l].cuda() for l in plan.layers]
+    t = [te[l].cuda() for l in plan.layers]
+    mask = am.cuda()
+    results = []
+    for no_tail in (0, 1):
+        _tune(cabi.TUNE_NO_TAIL, no_tail)
+        try:
+            g = [torch.empty_like(x) for x in s]
+            both = torch.empty((2, B, 256 + txt), dtype=torch.int64, device="cuda")
+            out, scale, ln = distill_fused(s, t, g, mask, plan, group=False, mask_out=(both[0], both[1]))
+            torch.cuda.synchronize()
+            results.append((out.clone(), g, both))
+        finally:
+            _tune(cabi.TUNE_NO_TAIL, 0)
+    assert torch.equal(results[0][0], results[1][0])
+    assert all(torch.equal(a, b) for a, b in zip(results[0][1], results[1][1]))
+    assert torch.equal(results[0][2], results[1][2])
+    ref = O.forward_backward(st, te, am, cfg)
+    assert float(results[0][0][0]) == pytest.approx(float(ref["loss"]), rel=2e-3)
+    for l, gl in zip(plan.layers, results[0][1]):
+        assert rel_err(gl.float().cpu(), ref["grads"][l].float()) < 2e-3
+
+
 def test_tail_counters_are_left_clean():
     """The arrival counters are taken round-robin and reset by the last CTA: many more steps than counters,
     alternating shapes and streams, all give the same bits."""
