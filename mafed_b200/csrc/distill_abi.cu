@@ -186,16 +186,21 @@ int launch_generic(const PathParams& p, int pass, cudaStream_t st) {
   return (int)cudaPeekAtLastError();
 }
 
-bool tma_geometry(const PathParams& p, int pass, TmaGeom& geo) {
+bool tma_geometry(const PathParams& p, int pass, TmaGeom& geo, int loss = MAFED_LOSS_MSE) {
   const DeviceInfo& dv = device_info();
   const long long row_bytes = (long long)p.n_chunks * 16;
   if (row_bytes > 32768) return false;
   const long long budget = (long long)dv.smem_optin - 16 * 1024;  // static smem + slack
   int rows = g_tune[kTuneTmaRows + pass].load();
+  bool cosine_fine = false;
   if (rows <= 0) {
     // Measured on B200 (profiles/r01_call3_sweep_step.json): a ring of 2 stages x 64-72 KB per SM is the
     // sweet spot for every pass; deeper rings (>= 192 KB in flight per SM) cost 4-8 % of HBM throughput.
-    const long long stage_target = 72 * 1024;
+    // The cosine gradient needs two sweeps over a row with a warp reduction in between, so a stage drains more
+    // slowly: with rows >= 4 KB a finer ring (4 stages x 32 KB) keeps more rows in different phases at once --
+    // 5-8 % faster on the 1B shape on two boxes (profiles/r01b_sweep_ring*.json), neutral or worse for short rows.
+    cosine_fine = loss == MAFED_LOSS_COSINE && pass != kPassFwd && row_bytes >= 4096;
+    const long long stage_target = cosine_fine ? 32 * 1024 : 72 * 1024;
     rows = (int)(stage_target / (2 * row_bytes));
     if (rows >= 8) rows &= ~7;
   }
@@ -206,7 +211,7 @@ bool tma_geometry(const PathParams& p, int pass, TmaGeom& geo) {
   geo.rows = rows;
   geo.stage_bytes = (int)(2 * rows * row_bytes);
   int stages = g_tune[kTuneTmaStages + pass].load();
-  if (stages <= 0) stages = (2 * geo.stage_bytes >= 96 * 1024) ? 2 : 3;
+  if (stages <= 0) stages = cosine_fine ? 4 : ((2 * geo.stage_bytes >= 96 * 1024) ? 2 : 3);
   if (stages > kTmaMaxStages) stages = kTmaMaxStages;
   while (stages > 1 && (long long)stages * geo.stage_bytes > budget) --stages;
   geo.stages = stages;
@@ -262,10 +267,12 @@ int dispatch_typed(PathParams& p, bool vector_ok, int pass, cudaStream_t st) {
   if (variant == 0) variant = 2;
   if (variant == 2) {
     TmaGeom geo;
-    if (tma_geometry(p, pass, geo)) {
+    if (tma_geometry(p, pass, geo, LOSS)) {
       // 16 consumer warps: two stages are drained concurrently when a stage holds <= 8 rows (+2.6 % on the
       // 1B shape, neutral elsewhere; profiles/r01_call4_sweep_extra.json)
-      if (g_tune[kTuneTmaWarps].load() == 8) return launch_tma<T, LOSS, 8>(p, geo, pass, st);
+      const int ncw = g_tune[kTuneTmaWarps].load();
+      if (ncw == 4) return launch_tma<T, LOSS, 4>(p, geo, pass, st);
+      if (ncw == 8) return launch_tma<T, LOSS, 8>(p, geo, pass, st);
       return launch_tma<T, LOSS, 16>(p, geo, pass, st);
     }
   }
@@ -309,7 +316,7 @@ bool uses_tma(const mafed_shape_t& sh, const PathParams& p, int pass) {
   PathParams q = p;
   q.n_chunks = (int)((size_t)sh.D * es / 16);
   TmaGeom geo;
-  return tma_geometry(q, pass, geo);
+  return tma_geometry(q, pass, geo);   // eligibility does not depend on the loss kind
 }
 
 // Common argument checks + pointer-table copy for the three streaming passes.

@@ -157,7 +157,11 @@ __device__ __forceinline__ void tma_tail(const PathParams& p, const double* coun
   __shared__ EpiSmem s_epi;
   __threadfence();  // this thread's partial-sum stores are visible device-wide before the arrival below
   named_bar_sync(1, NT);
-  if (threadIdx.x == 0) s_last = atomicAdd(p.tail_done, 1u) == gridDim.x - 1u;
+  if (threadIdx.x == 0) {
+    __threadfence();  // release: the CTA's stores (ordered before this point by the barrier) precede the arrival
+    s_last = atomicAdd(p.tail_done, 1u) == gridDim.x - 1u;
+    __threadfence();  // acquire: the other CTAs' stores are visible after the last arrival is observed
+  }
   named_bar_sync(1, NT);
   if (!s_last) return;
   __threadfence();
