@@ -422,7 +422,24 @@ def main():
     fwd_ms, bwd_ms, two_raw_ms = stage_loop(two_pass_step)
     fused_ms, fixup_ms, one_raw_ms = stage_loop(one_pass_step)
     two_api_ms, _, _ = api_loop(False)
+    peer = None
+    if world > 1:
+        from mafed_b200.comm import get_peer_comm
+        peer = get_peer_comm(None)
+    trace0 = peer.trace() if peer is not None else None
     api_ms, sampler, loss = api_loop(True)          # the product default: the headline `value`
+    trace1 = peer.trace() if peer is not None else None
+    uncoupled = None
+    if world > 1:
+        # the same API step with the exchange switched off (per-rank loss), all ranks at once: what every GPU does
+        # on its own.  The coupled step cannot be faster than the slowest of these.
+        fd.process_group = False
+        own_ms, _, _ = api_loop(True)
+        fd.process_group = None
+        own = torch.tensor([own_ms / args.steps], dtype=torch.float64, device=device)
+        every = [torch.zeros_like(own) for _ in range(world)]
+        dist.all_gather(every, own)
+        uncoupled = [float(x) for x in every]
     t = torch.tensor([api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, fixup_ms],
                      dtype=torch.float64, device=device)
     if world > 1:
@@ -486,6 +503,20 @@ def main():
                                                "sums in its last CTA" if peer_path else "nccl allreduce"),
         "loss": float(loss.detach()),
     }
+    if trace0 is not None:
+        # SM cycles the in-kernel exchanges took on rank 0 (mafed_comm_trace), per step, in us at the sampled SM clock
+        mhz = float(sampler.summary().get("sm_mhz") or 1900.0)
+        calls = max(1, trace1[3] - trace0[3])
+        line["exchange_trace_us"] = {
+            "counts_exchange_in_fused_kernel": (trace1[0] - trace0[0]) / calls / mhz,
+            "sums_publish_in_tail": (trace1[1] - trace0[1]) / calls / mhz,
+            "sums_wait_for_peers_in_tail": (trace1[2] - trace0[2]) / calls / mhz,
+            "steps_traced": calls}
+    if uncoupled is not None:
+        line["uncoupled_ms_per_rank"] = uncoupled
+        line["uncoupled_note"] = ("API step with the exchange off, all ranks running at once; the coupled step waits for "
+                                  "the slowest GPU every step: ms_per_step vs max(uncoupled) is the cost of the exchange "
+                                  "itself, max(uncoupled) vs the 1-GPU run is GPU-to-GPU variation")
     line["clocks"] = sampler.summary()
 
     # ---- (2) end to end with HOST buffers (pinned): H2D inputs, step, D2H gradients + loss

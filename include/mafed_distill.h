@@ -156,7 +156,8 @@ int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_p
  * mafed_b200/comm.py) and every rank maps its peers' mailboxes.  mafed_distill_scalar_stage_comm is
  * mafed_distill_scalar_stage with a one-shot SUM-allreduce of the selected part of the sums vector
  * (MAFED_COMM_SUMS: [0, 2L), MAFED_COMM_COUNTS: [2L, 2L+2)) performed inside the same kernel with NVLink
- * peer stores + flags, after REDUCE/COUNTS and before LOSSES/SCALE.  Results are bit-identical on all
+ * peer stores of self-validating words (value halves tagged with the epoch; no fence, no flag), after
+ * REDUCE/COUNTS and before LOSSES/SCALE.  Results are bit-identical on all
  * ranks; spins are bounded (mafed_comm_status reports a timeout), `sums` must not be NULL. */
 typedef struct mafed_comm mafed_comm_t;
 enum { MAFED_COMM_SUMS = 1, MAFED_COMM_COUNTS = 2 };
@@ -164,6 +165,9 @@ int mafed_comm_handle_bytes(void);
 int mafed_comm_create(int world, int rank, void* ipc_handle_out, mafed_comm_t** out);
 int mafed_comm_connect(mafed_comm_t* comm, const void* all_handles /* world x handle_bytes, rank order */);
 int mafed_comm_status(mafed_comm_t* comm, int* status_out /* 0 ok, 1 a peer timed out */);
+/* SM-cycle totals since creation (synchronises the device): [0] in-kernel counts exchange as seen by CTA 0,
+ * [1] own peer stores of a sums exchange, [2] waiting for the peers' vectors, [3] sums exchanges. */
+int mafed_comm_trace(mafed_comm_t* comm, unsigned long long* out4);
 int mafed_comm_destroy(mafed_comm_t* comm);
 int mafed_distill_scalar_stage_comm(const mafed_shape_t* shape, const mafed_weights_t* weights, int flags,
                                     const int64_t* attn_mask, const void* ws, double* sums, float* out,

@@ -31,6 +31,12 @@ class PeerComm:
         cabi.check(cabi.load().mafed_comm_status(self.handle, ctypes.byref(out)), "mafed_comm_status")
         return out.value
 
+    def trace(self):
+        """SM-cycle totals ``[counts exchange, publish, wait for peers, sums exchanges]`` (synchronises the device)."""
+        out = (ctypes.c_ulonglong * 4)()
+        cabi.check(cabi.load().mafed_comm_trace(self.handle, out), "mafed_comm_trace")
+        return list(out)
+
     def close(self):
         if self.handle:
             cabi.load().mafed_comm_destroy(self.handle)

@@ -364,13 +364,11 @@ CommDev comm_dev(const mafed_comm* c) {
   if (c == nullptr || c->world <= 1) return d;
   d.world = c->world;
   d.rank = c->rank;
-  for (int r = 0; r < c->world; ++r) {
-    d.data[r] = reinterpret_cast<double*>(c->peers[r]);
-    d.flags[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(c->peers[r]) + kCommDataBytes);
-  }
-  char* tail = reinterpret_cast<char*>(c->local) + kCommDataBytes + kCommFlagBytes;
+  for (int r = 0; r < c->world; ++r) d.ll[r] = reinterpret_cast<unsigned long long*>(c->peers[r]);
+  char* tail = reinterpret_cast<char*>(c->local) + kCommDataBytes;
   d.epoch = reinterpret_cast<unsigned long long*>(tail);
   d.status = reinterpret_cast<int*>(tail + 16);
+  d.trace = reinterpret_cast<unsigned long long*>(tail + 32);
   return d;
 }
 
@@ -596,8 +594,14 @@ int mafed_comm_connect(mafed_comm_t* c, const void* all_handles) {
 
 int mafed_comm_status(mafed_comm_t* c, int* status_out) {
   if (!c || !status_out) return MAFED_E_ARG;
-  const char* tail = reinterpret_cast<const char*>(c->local) + kCommDataBytes + kCommFlagBytes;
+  const char* tail = reinterpret_cast<const char*>(c->local) + kCommDataBytes;
   return (int)cudaMemcpy(status_out, tail + 16, sizeof(int), cudaMemcpyDeviceToHost);
+}
+
+int mafed_comm_trace(mafed_comm_t* c, unsigned long long* out4) {
+  if (!c || !out4) return MAFED_E_ARG;
+  const char* tail = reinterpret_cast<const char*>(c->local) + kCommDataBytes;
+  return (int)cudaMemcpy(out4, tail + 32, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
 }
 
 int mafed_comm_destroy(mafed_comm_t* c) {

@@ -1,15 +1,18 @@
-// One-shot, latency-bound allreduce of <= 130 doubles over NVLink peer memory, executed INSIDE the
-// single-CTA scalar stage (so the distributed step has the same launch count as the single-GPU step and
-// no NCCL call on its critical path).
+// One-shot, latency-bound allreduce of <= 130 doubles over NVLink peer memory, executed INSIDE the path's own
+// kernels (so the distributed step has the same launch count as the single-GPU step and no NCCL call on its
+// critical path).
 //
 // Every rank owns a small cudaMalloc'ed mailbox that its peers map with CUDA IPC:
-//   data  [2 parities][world][kCommSlots] doubles   -- slot [parity][r] is written only by rank r
-//   flags [2 parities][world] uint64                 -- epoch number, written by rank r after its data
-// A collective with epoch e: rank r stores its vector into slot [e&1][r] of EVERY rank's mailbox (NVLink
-// peer stores), fences system-wide, then publishes e into flag [e&1][r] of every mailbox; it then spins on
-// its OWN flags until all ranks have published e and sums the slots in rank order -- a fixed order, so all
-// ranks obtain bit-identical results.  Two parities suffice: a rank can be at most one epoch ahead of the
-// slowest rank, because finishing epoch e requires every rank to have entered epoch e.
+//   ll [2 parities][world][kCommSlots][2] uint64   -- slot [parity][r] is written only by rank r
+// Each double travels as two self-validating 8-byte words {32 data bits | 32-bit epoch tag} (the "LL" scheme of
+// NCCL's low-latency protocol): an aligned 8-byte store is never torn, so a word whose tag equals the current
+// epoch carries valid data.  No fence and no separate flag: a sender just fires its stores at every peer's
+// mailbox (one NVLink one-way trip, ~1-2 us) and goes on; a receiver polls the words of its OWN mailbox
+// (local L2) until the tags match and sums the values in rank order -- a fixed order, so all ranks obtain
+// bit-identical results.  (The first version stored data, fenced system-wide and then published a flag: the fence
+// alone cost ~4 us per exchange, `mafed_comm_trace`.)  Two parities suffice: a rank can be at most one epoch ahead
+// of the slowest rank, because finishing epoch e requires every rank to have entered epoch e; a slot therefore
+// still holds tag e-2 (or 0) until its owner writes epoch e.
 // The epoch counter lives in device memory and is bumped by the kernel, so the sequence is CUDA-graph safe.
 // Spins are bounded (~2 s): on timeout the kernel records an error code and goes on, it never hangs the GPU.
 #pragma once
@@ -17,17 +20,33 @@
 
 namespace mafed {
 
-constexpr size_t kCommDataBytes = sizeof(double) * 2 * kCommMaxRanks * kCommSlots;
-constexpr size_t kCommFlagBytes = sizeof(unsigned long long) * 2 * kCommMaxRanks;
-constexpr size_t kCommMailboxBytes = kCommDataBytes + kCommFlagBytes + 64;  // + epoch + status
+constexpr size_t kCommDataBytes = sizeof(unsigned long long) * 2 * 2 * kCommMaxRanks * kCommSlots;
+constexpr size_t kCommMailboxBytes = kCommDataBytes + 64;  // + epoch, status, trace
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+__device__ __forceinline__ uint32_t ll_tag(unsigned long long epoch) { return (uint32_t)epoch | 0x80000000u; }
+
+// Word pair of slot k of rank r's vector in a mailbox.
+__device__ __forceinline__ unsigned long long* ll_slot(unsigned long long* mailbox, int parity, int r, int k) {
+  return mailbox + (((size_t)parity * kCommMaxRanks + r) * kCommSlots + k) * 2;
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, uint32_t tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (b & 0xffffffffull) | ((unsigned long long)tag << 32);
+  const unsigned long long w1 = (b >> 32) | ((unsigned long long)tag << 32);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" :: "l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+
+// Spin until both words of `slot` carry `tag`; returns the value (0 and *status = 1 after the spin bound).
+__device__ __forceinline__ double ll_wait(const unsigned long long* slot, uint32_t tag, int* status) {
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+    if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag)
+      return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    if (clock64() - t0 > kCommTimeoutCycles) { *status = 1; return 0.0; }
+  }
 }
 
 // How the threads taking part in a scalar stage synchronise: the whole CTA (stand-alone k_epilogue) or the
@@ -48,6 +67,7 @@ template <int NT, typename Sync>
 __device__ __forceinline__ void peer_allreduce(const CommDev& c, double* vals, int n, int tid, Sync sync,
                                                unsigned long long epoch = 0ull) {
   __shared__ unsigned long long s_epoch;
+  const long long t_in = clock64();
   sync();
   if (tid == 0) {
     if (epoch == 0ull) s_epoch = ++(*c.epoch);
@@ -56,32 +76,27 @@ __device__ __forceinline__ void peer_allreduce(const CommDev& c, double* vals, i
   sync();
   const unsigned long long e = s_epoch;
   const int par = (int)(e & 1ull);
-  // 1. scatter my vector into my slot of every mailbox
+  const uint32_t tag = ll_tag(e);
+  // 1. fire my vector into my slot of every mailbox (peer stores over NVLink; my own included)
   for (int i = tid; i < n * c.world; i += NT) {
     const int peer = i / n, k = i - peer * n;
-    c.data[peer][((size_t)par * kCommMaxRanks + c.rank) * kCommSlots + k] = vals[k];
+    ll_store(ll_slot(c.ll[peer], par, c.rank, k), vals[k], tag);
   }
-  __threadfence_system();
-  sync();
-  // 2. publish
-  if (tid < c.world) st_release_sys(c.flags[tid] + par * kCommMaxRanks + c.rank, e);
-  // 3. wait for everybody's vector to land in my mailbox
-  if (tid < c.world) {
-    const unsigned long long* f = c.flags[c.rank] + par * kCommMaxRanks + tid;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) < e) {
-      if (clock64() - t0 > kCommTimeoutCycles) { *c.status = 1; break; }
-    }
-  }
-  sync();
-  // 4. reduce in rank order (identical on every rank)
-  const double* mine = c.data[c.rank] + (size_t)par * kCommMaxRanks * kCommSlots;
+  const long long t_pub = clock64();
+  sync();  // every thread has read its vals[] before they are overwritten below
+  // 2. element k: wait for every rank's word pair in my own mailbox, sum in rank order (identical on every rank)
   for (int k = tid; k < n; k += NT) {
     double acc = 0.0;
-    for (int r = 0; r < c.world; ++r) acc += __ldcg(mine + (size_t)r * kCommSlots + k);  // L2: peers wrote it
+    for (int r = 0; r < c.world; ++r) acc += ll_wait(ll_slot(c.ll[c.rank], par, r, k), tag, c.status);
     vals[k] = acc;
   }
   sync();
+  if (tid == 0) {   // where the time of an exchange goes (mafed_comm_trace): own stores vs waiting for the peers
+    const long long t_seen = clock64();
+    c.trace[1] += (unsigned long long)(t_pub - t_in);
+    c.trace[2] += (unsigned long long)(t_seen - t_pub);
+    c.trace[3] += 1ull;
+  }
 }
 
 }  // namespace mafed

@@ -26,10 +26,10 @@ constexpr int kCommSlots = 2 * kMaxLayers + 2;  // one full `sums` vector
 constexpr long long kCommTimeoutCycles = 4000000000LL;
 
 struct CommDev {
-  double* data[kCommMaxRanks];              // mailbox data region of every rank (peer-mapped; [rank] is local)
-  unsigned long long* flags[kCommMaxRanks]; // mailbox flag region of every rank
+  unsigned long long* ll[kCommMaxRanks];    // mailbox of every rank (peer-mapped; [rank] is local), see distill_comm.cuh
   unsigned long long* epoch;                // local: collectives issued so far
   int* status;                              // local: 0 ok, 1 timeout
+  unsigned long long* trace;                // local: SM-cycle totals [counts exchange, publish, wait for peers, calls]
   int world;                                // 0 = no communicator (single rank)
   int rank;
 };

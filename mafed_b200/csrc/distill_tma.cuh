@@ -338,36 +338,34 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
     for (int i = 0; i < NCW; ++i) n_text_local += s_cnt[i];
     double n_text = (double)n_text_local, n_vis_rows = p.n_vis_rows;
     if (p.comm.world > 1) {
-      // Batch-sharded step: the two token counts are exchanged right here.  CTA 0 stores this rank's counts
-      // into every rank's mailbox and publishes the epoch; every CTA then waits on its OWN rank's mailbox
-      // (local L2) for all peers and sums in rank order.  The NVLink round trip hides behind the first tiles.
+      // Batch-sharded step: the two token counts are exchanged right here.  CTA 0 fires this rank's counts into
+      // every rank's mailbox as self-validating words (distill_comm.cuh: no fence, no flag); every CTA then polls
+      // its OWN rank's mailbox (local L2) for all peers and sums in rank order.  The one-way NVLink trip hides
+      // behind the first tiles.
       const CommDev& c = p.comm;
+      const long long t_x0 = clock64();
       const unsigned long long e = p.comm_epoch;
       const int par = (int)(e & 1ull);
+      const uint32_t tag = ll_tag(e);
+      __shared__ double s_peer[kCommMaxRanks][2];
       if (blockIdx.x == 0) {
         if ((int)threadIdx.x < 2 * c.world) {
           const int peer = threadIdx.x >> 1, k = threadIdx.x & 1;
-          c.data[peer][((size_t)par * kCommMaxRanks + c.rank) * kCommSlots + k] = k == 0 ? n_text : n_vis_rows;
+          ll_store(ll_slot(c.ll[peer], par, c.rank, k), k == 0 ? n_text : n_vis_rows, tag);
         }
-        __threadfence_system();
-        named_bar_sync(1, NCW * 32);
-        if ((int)threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + par * kCommMaxRanks + c.rank, e);
         if (threadIdx.x == 0) *c.epoch = e;   // keep the device-side counter of the scalar stages in step
       }
-      if ((int)threadIdx.x < c.world) {
-        const unsigned long long* f = c.flags[c.rank] + par * kCommMaxRanks + threadIdx.x;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) < e) {
-          if (clock64() - t0 > kCommTimeoutCycles) { *c.status = 1; break; }
-        }
+      if ((int)threadIdx.x < 2 * c.world) {
+        const int r = threadIdx.x >> 1, k = threadIdx.x & 1;
+        s_peer[r][k] = ll_wait(ll_slot(c.ll[c.rank], par, r, k), tag, c.status);
       }
       named_bar_sync(1, NCW * 32);
-      const double* mine = c.data[c.rank] + (size_t)par * kCommMaxRanks * kCommSlots;
+      if (blockIdx.x == 0 && threadIdx.x == 0) c.trace[0] += (unsigned long long)(clock64() - t_x0);
       n_text = 0.0;
       n_vis_rows = 0.0;
       for (int r = 0; r < c.world; ++r) {
-        n_text += __ldcg(mine + (size_t)r * kCommSlots);
-        n_vis_rows += __ldcg(mine + (size_t)r * kCommSlots + 1);
+        n_text += s_peer[r][0];
+        n_vis_rows += s_peer[r][1];
       }
     }
     if (threadIdx.x == 0) { s_counts[0] = n_text; s_counts[1] = n_vis_rows; }
