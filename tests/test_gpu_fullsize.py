@@ -1,4 +1,4 @@
-"""BASELINE.json's full sizes (C2, C3-lite, C4 per-GPU shard): size-independent properties plus a plain
+"""BASELINE.json's full sizes (C2, C3, C4 per-GPU shard, a C5 sweep point with text:vision 1:1): size-independent properties plus a plain
 PyTorch fp32 restatement of the same op evaluated on the GPU layer by layer."""
 import pytest
 import torch
@@ -12,6 +12,9 @@ CONFIGS = {
     # name: (tuple_len, num_hidden_layers (ref rule L-1), B, txt, D)
     "C2-base-b128": (13, 11, 128, 32, 768),
     "C4-1b-shard-b64": (17, 15, 64, 32, 2048),
+    "C3-410m-b256": (25, 23, 256, 32, 1024),
+    # C5: 256 visual + 256 text tokens; 96 x 256 mask entries > 16 Ki -> counts from a prologue launch
+    "C5-1b-b96-txt256": (17, 15, 96, 256, 2048),
 }
 
 
