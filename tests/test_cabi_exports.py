@@ -37,6 +37,15 @@ def test_argument_errors_without_a_gpu():
     ok = cabi.make_shape(1, 1, 4, 2, 8, cabi.F32, cabi.LOSS_MSE)
     assert lib.mafed_distill_fwd(ctypes.byref(ok), None, None, None, None, None) == -1  # null pointer tables
     assert lib.mafed_distill_set_variant(9) == -1
+    # the one-call step: weights and the output vector are mandatory, the two masks come as a pair
+    w = cabi.make_weights(cabi.MODW_EQUAL, 1.0, [1.0])
+    one = ctypes.c_float(1.0)
+    assert lib.mafed_distill_step(ctypes.byref(ok), None, None, None, None, None, one, None, None, None, None, None,
+                                  None, None, None) == -1
+    assert lib.mafed_distill_step(ctypes.byref(ok), None, None, None, None, ctypes.byref(w), one, None, 8, None, None,
+                                  8, None, None, None) == -1
+    assert lib.mafed_distill_fwd_step(ctypes.byref(ok), None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.mafed_comm_trace(None, None) == -1
 
 
 def test_sass_is_sm100_and_uses_bulk_copies():
