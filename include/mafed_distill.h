@@ -174,11 +174,11 @@ int mafed_distill_scalar_stage_comm(const mafed_shape_t* shape, const mafed_weig
                                     float* bwd_scale, mafed_comm_t* comm, int comm_what, void* stream);
 
 /* mafed_distill_fused for the batch-sharded step: with `comm` (and `weights`) the exchange of the two token
- * counts happens INSIDE the fused kernel -- CTA 0 stores this rank's counts into every peer mailbox, all
- * CTAs wait on the local mailbox and derive the scale table -- so the step needs no prologue launch and the
- * NVLink round trip hides behind the first tiles.  The epoch of this exchange is tracked on the host (one per
- * call), so this entry is not CUDA-graph replayable; under capture use mafed_distill_scalar_stage_comm
- * (prologue) + mafed_distill_fused(weights = NULL).  comm == NULL behaves like mafed_distill_fused. */
+ * counts happens INSIDE the fused kernel -- CTA 0 fires this rank's counts into every peer mailbox, all CTAs poll
+ * the local mailbox and derive the scale table -- so the step needs no prologue launch and the NVLink trip hides
+ * behind the first tiles.  The epoch of the exchange is the device-side counter + 1, read by every CTA at its
+ * start and advanced by the last CTA to finish, so the call is CUDA-graph replayable.  comm == NULL behaves like
+ * mafed_distill_fused. */
 int mafed_distill_fused_comm(const mafed_shape_t* shape, const void* const* student_ptrs,
                              const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
                              const mafed_weights_t* weights, float* bwd_scale, float assumed_grad_out, void* ws,
@@ -193,10 +193,10 @@ int mafed_distill_fused_comm(const mafed_shape_t* shape, const void* const* stud
  * communicator it also exchanges the 2L sums with the peers there.  Other shapes run the same step as the
  * separate launches above.  out[1+3L] as in LOSSES; bwd_scale[2L] is written for the later fix-up
  * (mafed_distill_bwd with skip_if_equals); sums (optional single-rank, required with comm) receives the global
- * [2L+2] vector; lang_mask / image_mask (both or neither, int64 [B, T]) are optional.  Like
- * mafed_distill_fused_comm the sharded form tracks its epochs on the host (not CUDA-graph replayable).
+ * [2L+2] vector; lang_mask / image_mask (both or neither, int64 [B, T]) are optional.  All exchange epochs live
+ * on the device: the sharded forms are CUDA-graph replayable too.
  * mafed_distill_fwd_step is the two-pass form's first half: mafed_distill_fwd + REDUCE|COUNTS|LOSSES|SCALE in
- * one launch (sharded: sums and counts exchanged in the tail on the device-side epoch counter, graph-safe). */
+ * one launch (sharded: sums and counts exchanged in the tail). */
 int mafed_distill_step(const mafed_shape_t* shape, const void* const* student_ptrs,
                        const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
                        const mafed_weights_t* weights, float assumed_grad_out, void* ws, float* out,

@@ -101,13 +101,16 @@ long long mask_entries(const mafed_shape_t& sh) { return needs_mask(sh) ? (long 
 double vis_rows(const mafed_shape_t& sh) { return sh.cls ? (double)sh.B : (double)sh.B * (double)sh.n_vis; }
 
 // Arrival counters of the in-kernel tail (distill_tma.cuh).  A counter is zero whenever no kernel is using it
-// (the last CTA resets it), so launches take them round-robin: two kernels can only share one if 256 tailed
-// launches are in flight at once on one device, and each of them is a persistent whole-GPU kernel.
+// (the last CTA resets it), so launches take them round-robin: two kernels can only share one if 128 tailed
+// launches are in flight at once on one device, and each of them is a persistent whole-GPU kernel.  Launches
+// recorded into a CUDA graph keep their counter for every replay, so they draw from a separate half of the
+// pool: an eager launch on another stream can never land on the counter of a graph that is replaying.
 constexpr unsigned kDoneSlots = 256;
 __device__ unsigned int g_tail_done[kDoneSlots];
 std::atomic<unsigned> g_tail_next{0};
+std::atomic<unsigned> g_tail_next_captured{0};
 
-unsigned int* next_tail_counter() {
+unsigned int* next_tail_counter(cudaStream_t st) {
   static unsigned int* base[16] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
@@ -116,7 +119,11 @@ unsigned int* next_tail_counter() {
     if (cudaGetSymbolAddress(&p, g_tail_done) != cudaSuccess) return nullptr;
     base[dev] = reinterpret_cast<unsigned int*>(p);
   }
-  return base[dev] + (g_tail_next.fetch_add(1) % kDoneSlots);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) return nullptr;
+  constexpr unsigned half = kDoneSlots / 2;
+  if (cap == cudaStreamCaptureStatusActive) return base[dev] + half + (g_tail_next_captured.fetch_add(1) % half);
+  return base[dev] + (g_tail_next.fetch_add(1) % half);
 }
 
 // ---------------------------------------------------------------- launch helpers
@@ -350,7 +357,6 @@ int fill_params(const mafed_shape_t* shape, const void* const* student_ptrs, con
 struct mafed_comm {
   int world = 0;
   int rank = 0;
-  unsigned long long host_epoch = 0;   // collectives enqueued so far (mirrors the device-side counter)
   void* local = nullptr;
   void* peers[mafed::kCommMaxRanks] = {};
 };
@@ -383,7 +389,6 @@ int launch_scalar_stage(const mafed_shape_t& sh, const mafed_weights_t* w, int f
     if (comm_what == (MAFED_COMM_SUMS | MAFED_COMM_COUNTS)) { e.a.comm_first = 0; e.a.comm_count = L2 + 2; }
     else if (comm_what == MAFED_COMM_SUMS) { e.a.comm_first = 0; e.a.comm_count = L2; }
     else if (comm_what == MAFED_COMM_COUNTS) { e.a.comm_first = L2; e.a.comm_count = 2; }
-    if (e.a.comm_count > 0) const_cast<mafed_comm*>(comm)->host_epoch += 1;
   }
   e.a.ws = reinterpret_cast<const float*>(ws);
   e.a.mask = mask;
@@ -424,43 +429,37 @@ int fused_impl(const mafed_shape_t* shape, const void* const* student_ptrs, cons
   p.ws = reinterpret_cast<float*>(ws);
   const bool sharded = comm != nullptr && comm->world > 1;
   const bool tma = uses_tma(*shape, p, kPassFused);
-  // With `tail` the last CTA of the TMA kernel reduces the partials and forms the losses (and exchanges the sums
-  // with the peers), and all CTAs write the modality masks: no epilogue or mask launch.
+  const bool want_tail = tail != nullptr && weights != nullptr && tma && !g_tune[kTuneNoTail].load();
+  const bool want_inline = weights != nullptr && tma && mask_entries(*shape) <= 16384 && !g_tune[kTuneNoInlineScale].load();
+  // The arrival counter: needed for the tail and, in a sharded step, for the in-kernel counts exchange (the last
+  // CTA advances the device-side epoch).
   unsigned int* done = nullptr;
-  if (tail != nullptr && weights != nullptr && tma && !g_tune[kTuneNoTail].load()) done = next_tail_counter();
-  if (done != nullptr) {
+  if (want_tail || (want_inline && sharded)) done = next_tail_counter((cudaStream_t)stream);
+  p.tail_done = done;
+  if (done != nullptr && want_tail) {
+    // the last CTA of the TMA kernel reduces the partials and forms the losses (and exchanges the sums with the
+    // peers); all CTAs write the modality masks: no epilogue or mask launch
     p.tail_flags = kEpiReduce | kEpiLosses;
-    p.tail_done = done;
     p.tail_out = tail->out;
     p.tail_sums = tail->sums;
     p.lang_mask_out = tail->lang_mask;
     p.image_mask_out = tail->image_mask;
+    p.tail_comm = sharded ? 1 : 0;
+    if (folded != nullptr) *folded = true;
+  }
+  if (weights != nullptr) {
     p.loss_kind = shape->loss_kind;
     p.n_mask = mask_entries(*shape);
     p.n_vis_rows = vis_rows(*shape);
     p.w = *weights;
-    if (sharded) {
-      p.comm = comm_dev(comm);
-      p.tail_comm = 1;
-    }
-    if (folded != nullptr) *folded = true;
-  }
-  if (weights != nullptr) {
+    if (sharded) p.comm = comm_dev(comm);
     // the scale table is this call's business.  Small masks: every CTA of the TMA kernel derives it itself while
-    // its first tiles are in flight (the whole step is ONE launch); otherwise one prologue launch, which leaves the
-    // counts in the ws header for the tail.
-    const long long n_mask = mask_entries(*shape);
-    if (n_mask <= 16384 && !g_tune[kTuneNoInlineScale].load() && tma) {
+    // its first tiles are in flight (the whole step is ONE launch; in a sharded step the counts exchange rides
+    // inside the kernel); otherwise one prologue launch, which leaves the counts in the ws header for the tail.
+    if (want_inline && (!sharded || done != nullptr)) {
       p.inline_scale = 1;
-      p.loss_kind = shape->loss_kind;
-      p.n_mask = n_mask;
-      p.n_vis_rows = vis_rows(*shape);
       p.bwd_scale_out = bwd_scale;
-      p.w = *weights;
-      if (sharded) {   // the counts exchange rides inside the kernel, on host-tracked epochs
-        p.comm = comm_dev(comm);
-        p.comm_epoch = ++comm->host_epoch;
-      }
+      p.comm_counts = sharded ? 1 : 0;
     } else {
       double* counts = reinterpret_cast<double*>(p.ws + kWsCountsAt);
       p.tail_counts_in = counts;
@@ -468,7 +467,6 @@ int fused_impl(const mafed_shape_t* shape, const void* const* student_ptrs, cons
                                nullptr, bwd_scale, (cudaStream_t)stream, comm, MAFED_COMM_COUNTS, counts);
       if (rc) return rc;
     }
-    if (done != nullptr && sharded) ++comm->host_epoch;   // the tail's sums exchange
   }
   return dispatch(*shape, p, kPassFused, (cudaStream_t)stream);
 }
@@ -711,7 +709,7 @@ int mafed_distill_fwd_step(const mafed_shape_t* shape, const void* const* studen
   p.ws = reinterpret_cast<float*>(ws);
   const int flags = MAFED_STAGE_REDUCE | MAFED_STAGE_COUNTS | MAFED_STAGE_LOSSES | (bwd_scale ? MAFED_STAGE_SCALE : 0);
   unsigned int* done = nullptr;
-  if (!g_tune[kTuneNoTail].load() && uses_tma(*shape, p, kPassFwd)) done = next_tail_counter();
+  if (!g_tune[kTuneNoTail].load() && uses_tma(*shape, p, kPassFwd)) done = next_tail_counter((cudaStream_t)stream);
   if (done != nullptr) {
     p.tail_flags = flags;
     p.tail_done = done;
@@ -722,10 +720,9 @@ int mafed_distill_fwd_step(const mafed_shape_t* shape, const void* const* studen
     p.n_mask = mask_entries(*shape);
     p.n_vis_rows = vis_rows(*shape);
     p.w = *weights;
-    if (sharded) {   // sums + counts exchange inside the tail, on the device-side epoch counter
+    if (sharded) {   // sums + counts exchange inside the tail
       p.comm = comm_dev(comm);
       p.tail_comm = 1;
-      comm->host_epoch += 1;
     }
     return dispatch(*shape, p, kPassFwd, (cudaStream_t)stream);
   }

@@ -61,8 +61,9 @@ struct SyncNamed {
 };
 
 // In-place SUM-allreduce of vals[0..n) (shared memory) across the communicator; threads tid = 0..NT-1 take
-// part.  `epoch` = 0: take the next epoch from the device-side counter (CUDA-graph safe); otherwise the
-// host-tracked epoch of this exchange (the counter is set to it).
+// part.  `epoch` = 0: take the next epoch from the device-side counter; otherwise use the given epoch (the one
+// after an earlier exchange of the same kernel) and set the counter to it.  Either way the epochs live on the
+// device only, so every sequence of exchanges is CUDA-graph replayable.
 template <int NT, typename Sync>
 __device__ __forceinline__ void peer_allreduce(const CommDev& c, double* vals, int n, int tid, Sync sync,
                                                unsigned long long epoch = 0ull) {

@@ -62,8 +62,10 @@ struct PathParams {
   double n_vis_rows;             // B * n_vis
   float* bwd_scale_out;          // CTA 0 publishes the table for the later backward fix-up
   mafed_weights_t w;
-  // batch-sharded one-pass step: the token counts are exchanged inside this kernel (comm.world > 1)
-  unsigned long long comm_epoch; // epoch of this exchange (host-tracked, = device epoch + 1)
+  // batch-sharded one-pass step: the token counts are exchanged inside this kernel (comm.world > 1).  Every CTA
+  // reads the device-side epoch counter at its start; only the LAST CTA to finish (tail) advances it, so all
+  // CTAs of a launch agree on the epoch and the sequence stays CUDA-graph replayable.
+  int comm_counts;               // 1: exchange the counts in this kernel (epoch = device-side counter + 1)
   CommDev comm;
   int load_policy;               // L2 eviction hint for student/teacher reads (CachePolicy)
   int store_policy;              // L2 eviction hint for gradient writes

@@ -33,7 +33,7 @@ struct EpiArgs {
   int flags;
   int comm_first;         // range of the sums vector to allreduce over the peer mailboxes
   int comm_count;         // (0 = no communication)
-  unsigned long long comm_epoch;  // 0: device-side epoch counter; else the host-tracked epoch of the exchange
+  unsigned long long comm_epoch;  // 0: next value of the device-side epoch counter; else the epoch to use (and store)
 };
 
 struct EpiParams {

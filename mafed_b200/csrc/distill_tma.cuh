@@ -152,7 +152,8 @@ __device__ __forceinline__ void tma_prologue(TmaSmem& sm, const TmaGeom& geo) {
 // peer exchange) -- what a separate single-CTA epilogue launch would do.  The order of the reduction does
 // not depend on which CTA is last, so results stay bit-reproducible.
 template <int NT>
-__device__ __forceinline__ void tma_tail(const PathParams& p, const double* counts_in) {
+__device__ __forceinline__ void tma_tail(const PathParams& p, const double* counts_in,
+                                         unsigned long long counts_epoch = 0ull) {
   __shared__ int s_last;
   __shared__ EpiSmem s_epi;
   __threadfence();  // this thread's partial-sum stores are visible device-wide before the arrival below
@@ -166,6 +167,11 @@ __device__ __forceinline__ void tma_tail(const PathParams& p, const double* coun
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x == 0) *p.tail_done = 0u;  // every other CTA has arrived: leave the counter clean for its next user
+  if (!p.tail_flags) {
+    // no scalar stage here; after an in-kernel counts exchange the epoch counter still has to move on
+    if (counts_epoch != 0ull && threadIdx.x == 0) *p.comm.epoch = counts_epoch;
+    return;
+  }
   EpiArgs a;
   a.ws = p.ws;
   a.mask = p.mask;
@@ -183,9 +189,10 @@ __device__ __forceinline__ void tma_tail(const PathParams& p, const double* coun
   a.flags = p.tail_flags;
   a.comm_first = 0;
   a.comm_count = p.tail_comm ? (2 * p.n_layers + ((p.tail_flags & kEpiCounts) ? 2 : 0)) : 0;
-  // after an in-kernel counts exchange (host-tracked epoch) the sums exchange is the next epoch; otherwise the
-  // device-side epoch counter is used
-  a.comm_epoch = p.comm_epoch != 0ull ? p.comm_epoch + 1ull : 0ull;
+  // after an in-kernel counts exchange at epoch e the sums exchange is e + 1 (and the counter becomes e + 1);
+  // otherwise the next value of the counter
+  a.comm_epoch = counts_epoch != 0ull ? counts_epoch + 1ull : 0ull;
+  if (counts_epoch != 0ull && a.comm_count == 0 && threadIdx.x == 0) *p.comm.epoch = counts_epoch;
   scalar_stage<NT>(a, p.comm, p.w, s_epi, (int)threadIdx.x, SyncNamed<NT>());
 }
 
@@ -270,7 +277,7 @@ k_fwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
   cta_sums_flush(sums, warp, lane, cur, acc_text, acc_vis);
   named_bar_sync(1, NCW * 32);
   cta_sums_store(sums, p.ws, p.n_layers, 0, NCW * 32);
-  if (p.tail_flags) tma_tail<NCW * 32>(p, nullptr);
+  if (p.tail_done != nullptr) tma_tail<NCW * 32>(p, nullptr);
 }
 
 // ---------------------------------------------------------------- backward
@@ -314,6 +321,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
   // L2-resident) and derive the table; CTA 0 publishes it for the later backward fix-up.
   __shared__ float s_scale[2 * kMaxLayers];
   __shared__ double s_counts[2];  // (global) token counts, kept for the tail
+  unsigned long long counts_epoch = 0ull;
   if (FUSED && p.lang_mask_out != nullptr) {
     // the masks the reference leaves in `batch` (distillation.py:134-144): a few hundred KB spread over all CTAs
     const long long n = p.n_rows;
@@ -337,14 +345,16 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
 #pragma unroll
     for (int i = 0; i < NCW; ++i) n_text_local += s_cnt[i];
     double n_text = (double)n_text_local, n_vis_rows = p.n_vis_rows;
-    if (p.comm.world > 1) {
+    if (p.comm.world > 1 && p.comm_counts) {
       // Batch-sharded step: the two token counts are exchanged right here.  CTA 0 fires this rank's counts into
       // every rank's mailbox as self-validating words (distill_comm.cuh: no fence, no flag); every CTA then polls
       // its OWN rank's mailbox (local L2) for all peers and sums in rank order.  The one-way NVLink trip hides
       // behind the first tiles.
       const CommDev& c = p.comm;
       const long long t_x0 = clock64();
-      const unsigned long long e = p.comm_epoch;
+      // nobody writes the counter before the last CTA's tail: every CTA of this launch reads the same value
+      const unsigned long long e = __ldcg(c.epoch) + 1ull;
+      counts_epoch = e;
       const int par = (int)(e & 1ull);
       const uint32_t tag = ll_tag(e);
       __shared__ double s_peer[kCommMaxRanks][2];
@@ -353,7 +363,6 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
           const int peer = threadIdx.x >> 1, k = threadIdx.x & 1;
           ll_store(ll_slot(c.ll[peer], par, c.rank, k), k == 0 ? n_text : n_vis_rows, tag);
         }
-        if (threadIdx.x == 0) *c.epoch = e;   // keep the device-side counter of the scalar stages in step
       }
       if ((int)threadIdx.x < 2 * c.world) {
         const int r = threadIdx.x >> 1, k = threadIdx.x & 1;
@@ -528,7 +537,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
     cta_sums_flush(sums, warp, lane, cur, acc_text, acc_vis);
     named_bar_sync(1, NCW * 32);
     cta_sums_store(sums, p.ws, p.n_layers, 0, NCW * 32);
-    if (p.tail_flags) tma_tail<NCW * 32>(p, p.inline_scale ? s_counts : p.tail_counts_in);
+    if (p.tail_done != nullptr) tma_tail<NCW * 32>(p, p.inline_scale ? s_counts : p.tail_counts_in, counts_epoch);
   }
 }
 

@@ -296,10 +296,10 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
         w = ctypes.byref(plan.weights())
         distributed, pg = resolve_group(group)
         peer = get_peer_comm(pg) if distributed else None
-        capturing = peer is not None and torch.cuda.is_current_stream_capturing()
-        if not distributed or (peer is not None and not capturing):
+        if not distributed or peer is not None:
             # one launch, on one GPU and across batch shards alike: with a communicator the counts are exchanged
-            # inside the kernel behind its first tiles and the sums by its last CTA (NVLink peer stores, no NCCL)
+            # inside the kernel behind its first tiles and the sums by its last CTA (NVLink peer stores, no NCCL;
+            # the epochs live on the device, so the step can be captured into a CUDA graph and replayed)
             sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev) if peer is not None else None
             lang, image = mask_out if mask_out is not None else (None, None)
             cabi.check(lib.mafed_distill_step(
@@ -311,18 +311,6 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
         if mask_out is not None:
             modality_masks_into(ln.mask, plan.n_vis, *mask_out)
         sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
-        if capturing:
-            # under CUDA-graph capture: device-side epochs only (prologue with the counts exchange)
-            cabi.check(lib.mafed_distill_scalar_stage_comm(
-                ln.shape_ref, w, cabi.STAGE_COUNTS | cabi.STAGE_SCALE, ln.mask_ptr, None, sums.data_ptr(), None,
-                bwd_scale.data_ptr(), peer.handle, cabi.COMM_COUNTS, stream), "prologue_comm")
-            cabi.check(lib.mafed_distill_fused(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr, None,
-                                               bwd_scale.data_ptr(), fixed, ws.data_ptr(), stream),
-                       "mafed_distill_fused")
-            cabi.check(lib.mafed_distill_scalar_stage_comm(
-                ln.shape_ref, w, cabi.STAGE_REDUCE | cabi.STAGE_LOSSES, None, ws.data_ptr(), sums.data_ptr(),
-                out.data_ptr(), None, peer.handle, cabi.COMM_SUMS, stream), "epilogue_comm")
-            return out, bwd_scale, ln
         # NCCL: counts allreduce -> scale table -> fused pass -> sums allreduce -> losses
         cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_COUNTS, ln.mask_ptr, None,
                                                   sums.data_ptr(), None, None, stream), "counts")
