@@ -1,11 +1,11 @@
 """Host-buffer entry to the distillation step: inputs and outputs live in (pinned) host memory.
 
 This is the end-to-end form of the path for callers whose hidden states are not already on the
-device: every step copies student / teacher / mask host -> device, runs the fused forward,
-epilogue and backward, and copies the gradients and the loss device -> host.  Layers are
-pipelined over three streams (copy-in, compute, copy-out) so that PCIe transfers in both directions
-overlap each other and the kernels; per layer the work is two C-ABI calls
-(``mafed_distill_fused`` + ``mafed_distill_epilogue`` with ``n_layers = 1``).
+device: every step copies student / teacher / mask host -> device, runs the one-pass step and copies
+the gradients and the loss device -> host.  Layers are pipelined over three streams (copy-in, compute,
+copy-out) so that PCIe transfers in both directions overlap each other and the kernels; per layer the
+work is one C-ABI call (``mafed_distill_step`` with ``n_layers = 1``: one kernel launch, including the
+cross-rank exchange of a batch-sharded run).
 
 The backward of a layer needs only the token counts and the host weight tables, not the other
 layers' sums, which is what makes the per-layer pipeline legal.
