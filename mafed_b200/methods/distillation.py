@@ -7,9 +7,11 @@ behind ``CLMethod["featdistill"]`` (``mafed/train.py:119-134``,
 
 What changed underneath: the reference loops over layers in Python and, per layer, builds two masks
 on the CPU, runs two masked token-loss passes through ~16 ATen kernels and synchronises the host for
-W&B.  Here one step is: one fused forward kernel over all selected layers, one single-CTA epilogue,
-one fused backward kernel -- no host synchronisation; the per-layer values the reference logs
-(``task_{k}/distill_loss_{layer}``) stay on the device and are logged one step late.
+W&B.  Here one step is ONE kernel launch over all selected layers (masks, gradient scale, loss sums,
+gradients and the loss algebra; ``mafed_distill_step``) plus a fix-up launch in ``backward`` that returns
+at once unless the upstream gradient differs from the assumed one -- no host synchronisation; the
+per-layer values the reference logs (``task_{k}/distill_loss_{layer}``) stay on the device and are
+logged one step late.
 """
 from __future__ import annotations
 
