@@ -62,3 +62,18 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(cabi, "LIB_PATH", str(tmp_path / "libmafed_distill.so"))
     with pytest.raises(cabi.MafedDistillError, match="no CPU / eager fallback"):
         cabi.load()
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/mafed_distill.h compiles as C99 (-pedantic) and a C program linked against the library can call
+    the ABI -- the non-Python binding route of INTEGRATION.md."""
+    build.build()
+    src = os.path.join(ROOT, "tests", "c", "cabi_consumer.c")
+    exe = str(tmp_path / "cabi_consumer")
+    lib_dir = os.path.dirname(cabi.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+           "-L", lib_dir, "-lmafed_distill", f"-Wl,-rpath,{lib_dir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.strip() == "OK", run.stdout + run.stderr
