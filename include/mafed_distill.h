@@ -158,12 +158,16 @@ int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_p
  * (MAFED_COMM_SUMS: [0, 2L), MAFED_COMM_COUNTS: [2L, 2L+2)) performed inside the same kernel with NVLink
  * peer stores of self-validating words (value halves tagged with the epoch; no fence, no flag), after
  * REDUCE/COUNTS and before LOSSES/SCALE.  Results are bit-identical on all
- * ranks; spins are bounded (mafed_comm_status reports a timeout), `sums` must not be NULL. */
+ * ranks; spins are bounded (mafed_comm_set_timeout; mafed_comm_status reports a timeout), `sums` must not be NULL. */
 typedef struct mafed_comm mafed_comm_t;
 enum { MAFED_COMM_SUMS = 1, MAFED_COMM_COUNTS = 2 };
 int mafed_comm_handle_bytes(void);
 int mafed_comm_create(int world, int rank, void* ipc_handle_out, mafed_comm_t** out);
+/* all_handles == NULL: diagnostic loop-back (all peers map to the own mailbox; every exchange times out). */
 int mafed_comm_connect(mafed_comm_t* comm, const void* all_handles /* world x handle_bytes, rank order */);
+/* Spin bound of one in-kernel wait (default 60 s, or MAFED_B200_COMM_TIMEOUT_S at creation).  A wait that runs
+ * into it sets the status and yields NaN: the step's loss and gradients come out NaN instead of silently wrong. */
+int mafed_comm_set_timeout(mafed_comm_t* comm, double seconds);
 int mafed_comm_status(mafed_comm_t* comm, int* status_out /* 0 ok, 1 a peer timed out */);
 /* SM-cycle totals since creation (synchronises the device): [0] in-kernel counts exchange as seen by CTA 0,
  * [1] own peer stores of a sums exchange, [2] waiting for the peers' vectors, [3] sums exchanges. */

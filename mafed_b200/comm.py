@@ -31,6 +31,18 @@ class PeerComm:
         cabi.check(cabi.load().mafed_comm_status(self.handle, ctypes.byref(out)), "mafed_comm_status")
         return out.value
 
+    def set_timeout(self, seconds: float):
+        """Spin bound of one in-kernel wait (default 60 s, ``MAFED_B200_COMM_TIMEOUT_S``)."""
+        cabi.check(cabi.load().mafed_comm_set_timeout(self.handle, float(seconds)), "mafed_comm_set_timeout")
+
+    def check(self):
+        """Raise if a peer did not arrive within the spin bound in any exchange so far (the losses and gradients
+        of that step are NaN).  Synchronises the device: call it where the host reads results anyway."""
+        if self.status() != 0:
+            raise cabi.MafedDistillError(
+                f"rank {self.rank}: a peer did not reach a distillation exchange within the spin bound "
+                "(MAFED_B200_COMM_TIMEOUT_S); the results of that step are NaN")
+
     def trace(self):
         """SM-cycle totals ``[counts exchange, publish, wait for peers, sums exchanges]`` (synchronises the device)."""
         out = (ctypes.c_ulonglong * 4)()
@@ -76,6 +88,11 @@ def get_peer_comm(group=None) -> Optional[PeerComm]:
     if key not in _cache:
         _cache[key] = _build(group)
     return _cache[key]
+
+
+def peek_peer_comm(group=None) -> Optional[PeerComm]:
+    """The communicator of `group` if one has been built already (never builds one: not a collective call)."""
+    return _cache.get((id(group) if group is not None else 0, torch.cuda.current_device()))
 
 
 def reset():

@@ -3,6 +3,7 @@
 // kernels on the caller's stream.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "distill_common.cuh"
@@ -359,6 +360,9 @@ struct mafed_comm {
   int rank = 0;
   void* local = nullptr;
   void* peers[mafed::kCommMaxRanks] = {};
+  long long timeout_cycles = 0;
+  double cycles_per_second = 1.9e9;
+  bool loopback = false;
 };
 
 namespace mafed {
@@ -370,6 +374,7 @@ CommDev comm_dev(const mafed_comm* c) {
   if (c == nullptr || c->world <= 1) return d;
   d.world = c->world;
   d.rank = c->rank;
+  d.timeout_cycles = c->timeout_cycles;
   for (int r = 0; r < c->world; ++r) d.ll[r] = reinterpret_cast<unsigned long long*>(c->peers[r]);
   char* tail = reinterpret_cast<char*>(c->local) + kCommDataBytes;
   d.epoch = reinterpret_cast<unsigned long long*>(tail);
@@ -573,12 +578,34 @@ int mafed_comm_create(int world, int rank, void* ipc_handle_out, mafed_comm_t** 
   }
   memcpy(ipc_handle_out, &h, sizeof(h));
   c->peers[rank] = c->local;
+  int dev = 0, khz = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev) == cudaSuccess && khz > 0)
+    c->cycles_per_second = 1e3 * (double)khz;
+  double seconds = kCommDefaultTimeoutS;
+  if (const char* env = getenv("MAFED_B200_COMM_TIMEOUT_S")) {
+    const double v = atof(env);
+    if (v > 0.0) seconds = v;
+  }
+  c->timeout_cycles = (long long)(seconds * c->cycles_per_second);
   *out = c;
   return 0;
 }
 
+int mafed_comm_set_timeout(mafed_comm_t* c, double seconds) {
+  if (!c || !(seconds > 0.0)) return MAFED_E_ARG;
+  c->timeout_cycles = (long long)(seconds * c->cycles_per_second);
+  return 0;
+}
+
 int mafed_comm_connect(mafed_comm_t* c, const void* all_handles) {
-  if (!c || !all_handles) return MAFED_E_ARG;
+  if (!c) return MAFED_E_ARG;
+  if (!all_handles) {
+    // diagnostic loop-back: every "peer" is this rank's own mailbox.  Rank r only ever fills slot r, so the other
+    // ranks' slots stay empty and every exchange runs into the spin bound -- the way to test that bound on one GPU.
+    for (int r = 0; r < c->world; ++r) c->peers[r] = c->local;
+    c->loopback = true;
+    return 0;
+  }
   const char* hs = reinterpret_cast<const char*>(all_handles);
   for (int r = 0; r < c->world; ++r) {
     if (r == c->rank) continue;
@@ -605,7 +632,7 @@ int mafed_comm_trace(mafed_comm_t* c, unsigned long long* out4) {
 int mafed_comm_destroy(mafed_comm_t* c) {
   if (!c) return 0;
   for (int r = 0; r < c->world; ++r)
-    if (r != c->rank && c->peers[r]) cudaIpcCloseMemHandle(c->peers[r]);
+    if (!c->loopback && r != c->rank && c->peers[r]) cudaIpcCloseMemHandle(c->peers[r]);
   if (c->local) cudaFree(c->local);
   delete c;
   return 0;

@@ -14,7 +14,8 @@
 // of the slowest rank, because finishing epoch e requires every rank to have entered epoch e; a slot therefore
 // still holds tag e-2 (or 0) until its owner writes epoch e.
 // The epoch counter lives in device memory and is bumped by the kernel, so the sequence is CUDA-graph safe.
-// Spins are bounded (~2 s): on timeout the kernel records an error code and goes on, it never hangs the GPU.
+// Spins are bounded (60 s by default, mafed_comm_set_timeout): on timeout the kernel records an error code, returns
+// NaN for the missing values and goes on -- it never hangs the GPU, and the step's loss and gradients come out NaN.
 #pragma once
 #include "distill_common.cuh"
 
@@ -37,15 +38,20 @@ __device__ __forceinline__ void ll_store(unsigned long long* slot, double v, uin
   asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" :: "l"(slot), "l"(w0), "l"(w1) : "memory");
 }
 
-// Spin until both words of `slot` carry `tag`; returns the value (0 and *status = 1 after the spin bound).
-__device__ __forceinline__ double ll_wait(const unsigned long long* slot, uint32_t tag, int* status) {
+// Spin until both words of `slot` carry `tag`; returns the value.  After the spin bound: *status = 1 and NaN, so
+// that a peer that never arrived poisons the loss and the gradients visibly instead of leaving plausible numbers.
+__device__ __forceinline__ double ll_wait(const unsigned long long* slot, uint32_t tag, int* status,
+                                          long long timeout_cycles) {
   const long long t0 = clock64();
   for (;;) {
     unsigned long long w0, w1;
     asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
     if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag)
       return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-    if (clock64() - t0 > kCommTimeoutCycles) { *status = 1; return 0.0; }
+    if (clock64() - t0 > timeout_cycles) {
+      *status = 1;
+      return __longlong_as_double(0x7ff8000000000000LL);
+    }
   }
 }
 
@@ -88,7 +94,7 @@ __device__ __forceinline__ void peer_allreduce(const CommDev& c, double* vals, i
   // 2. element k: wait for every rank's word pair in my own mailbox, sum in rank order (identical on every rank)
   for (int k = tid; k < n; k += NT) {
     double acc = 0.0;
-    for (int r = 0; r < c.world; ++r) acc += ll_wait(ll_slot(c.ll[c.rank], par, r, k), tag, c.status);
+    for (int r = 0; r < c.world; ++r) acc += ll_wait(ll_slot(c.ll[c.rank], par, r, k), tag, c.status, c.timeout_cycles);
     vals[k] = acc;
   }
   sync();

@@ -23,13 +23,14 @@ constexpr int kWsCountsAt = 2;
 // Peer-memory communicator as the kernels see it (see distill_comm.cuh).
 constexpr int kCommMaxRanks = 16;
 constexpr int kCommSlots = 2 * kMaxLayers + 2;  // one full `sums` vector
-constexpr long long kCommTimeoutCycles = 4000000000LL;
+constexpr double kCommDefaultTimeoutS = 60.0;  // spin bound of an exchange (MAFED_B200_COMM_TIMEOUT_S / mafed_comm_set_timeout)
 
 struct CommDev {
   unsigned long long* ll[kCommMaxRanks];    // mailbox of every rank (peer-mapped; [rank] is local), see distill_comm.cuh
   unsigned long long* epoch;                // local: collectives issued so far
   int* status;                              // local: 0 ok, 1 timeout
   unsigned long long* trace;                // local: SM-cycle totals [counts exchange, publish, wait for peers, calls]
+  long long timeout_cycles;                 // spin bound of one wait, in SM cycles
   int world;                                // 0 = no communicator (single rank)
   int rank;
 };

@@ -366,7 +366,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
       }
       if ((int)threadIdx.x < 2 * c.world) {
         const int r = threadIdx.x >> 1, k = threadIdx.x & 1;
-        s_peer[r][k] = ll_wait(ll_slot(c.ll[c.rank], par, r, k), tag, c.status);
+        s_peer[r][k] = ll_wait(ll_slot(c.ll[c.rank], par, r, k), tag, c.status, c.timeout_cycles);
       }
       named_bar_sync(1, NCW * 32);
       if (blockIdx.x == 0 && threadIdx.x == 0) c.trace[0] += (unsigned long long)(clock64() - t_x0);

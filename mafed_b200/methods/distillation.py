@@ -316,11 +316,23 @@ class FeatureDistillation(CLStrategy):
         if _wandb is not None and getattr(_wandb, "run", None) is not None:
             _wandb.log({f"task_{task_id}/distill_loss_{l}": float(v) for l, v in zip(layers, host.tolist())})
 
+    def check_exchange(self):
+        """Batch-sharded runs: raise if a peer missed an in-kernel exchange (that step's results are NaN).
+        Synchronises the device; called where the host reads the losses anyway."""
+        from mafed_b200.comm import peek_peer_comm
+        group = self.process_group
+        if group is False:
+            return
+        peer = peek_peer_comm(None if group is None or group is True else group)
+        if peer is not None:
+            peer.check()
+
     def layer_loss_dict(self) -> Dict[str, float]:
         """The reference's W&B payload for the last step (synchronises the host)."""
         if self.last_layer_losses is None:
             return {}
         vals = self.last_layer_losses[: len(self.last_layers)].tolist()
+        self.check_exchange()
         return {f"task_{self.task_id}/distill_loss_{l}": v for l, v in zip(self.last_layers, vals)}
 
     # ------------------------------------------------------------------ checkpoint / resume

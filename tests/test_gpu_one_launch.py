@@ -208,3 +208,43 @@ def test_autograd_op_fills_the_batch_masks():
     lang, image = modality_masks(mask, 256)
     assert torch.equal(both[0], lang) and torch.equal(both[1], image)
     assert all(x.grad is not None for x in s)
+
+
+def test_missing_peer_poisons_the_step_instead_of_hanging():
+    """A rank whose peer never arrives: the in-kernel waits run into the spin bound, the status is set and the
+    loss comes out NaN (loop-back communicator of world 2 on one GPU, 50 ms bound)."""
+    import time
+    lib = cabi.load()
+    L, B, txt, D = 2, 3, 5, 512
+    st, te, am = _inputs(B, txt, D, L, torch.float32, seed=23)
+    _, plan = _plan(L, "mse", "equal")
+    s = [st[l].cuda() for l in plan.layers]
+    t = [te[l].cuda() for l in plan.layers]
+    n = len(s)
+    mask = am.cuda()
+    g = [torch.empty_like(x) for x in s]
+    handle = ctypes.c_void_p()
+    buf = ctypes.create_string_buffer(lib.mafed_comm_handle_bytes())
+    assert lib.mafed_comm_create(2, 0, buf, ctypes.byref(handle)) == 0
+    try:
+        assert lib.mafed_comm_connect(handle, None) == 0          # loop-back: rank 1 never writes its slots
+        assert lib.mafed_comm_set_timeout(handle, 0.05) == 0
+        shape = cabi.make_shape(n, B, 256 + txt, 256, D, cabi.F32, cabi.LOSS_MSE)
+        ws = torch.empty(lib.mafed_distill_ws_bytes(n), dtype=torch.uint8, device="cuda")
+        out = torch.zeros(1 + 3 * n, device="cuda")
+        scale = torch.empty(2 * n, device="cuda")
+        sums = torch.empty(2 * n + 2, dtype=torch.float64, device="cuda")
+        t0 = time.perf_counter()
+        rc = lib.mafed_distill_step(ctypes.byref(shape), cabi.ptr_array([x.data_ptr() for x in s]),
+                                    cabi.ptr_array([x.data_ptr() for x in t]), cabi.ptr_array([x.data_ptr() for x in g]),
+                                    mask.data_ptr(), ctypes.byref(plan.weights()), 1.0, ws.data_ptr(), out.data_ptr(),
+                                    scale.data_ptr(), sums.data_ptr(), None, None, handle,
+                                    torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert time.perf_counter() - t0 < 5.0                      # bounded: two waits of 50 ms, not a hang
+        status = ctypes.c_int(0)
+        assert lib.mafed_comm_status(handle, ctypes.byref(status)) == 0 and status.value == 1
+        assert torch.isnan(out[0]) and all(torch.isnan(x).any() for x in g)
+    finally:
+        lib.mafed_comm_destroy(handle)
