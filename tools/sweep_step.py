@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Steady-state step sweep: times whole steps (one-pass: prologue+fused+epilogue+fix-up; two-pass:
-fwd+epilogue+bwd) back to back, >= 100 iterations per point, every point measured `--repeats` times in
+"""Steady-state step sweep: times whole steps (one-pass: fused kernel + fix-up; two-pass: forward kernel +
+backward kernel; the scalar stages run inside the kernels' last CTA) back to back, >= 100 iterations per point, every point measured `--repeats` times in
 shuffled order, over TMA geometry and L2 eviction hints.
 
     python tools/sweep_step.py [--workloads C4,C2,C3] [--iters 100] [--repeats 2] [--mode one,two]
