@@ -22,7 +22,9 @@ TUNE_TMA_WARPS, TUNE_LDG_BLOCKS_PER_SM, TUNE_BWD_FORWARD_ORDER, TUNE_GRID_MUL = 
 TUNE_LOAD_POLICY, TUNE_STORE_POLICY = 13, 14   # 0 none, 1 evict_first, 2 evict_last, 3 evict_normal
 N_TUNE_KEYS = 18
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmafed_distill.so")
+# MAFED_B200_LIB: another build of the same C ABI (A/B measurements of two kernel versions, tools/ab_lib.py)
+LIB_PATH = os.environ.get("MAFED_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
+                                                            "libmafed_distill.so")
 
 EXPORTS = (
     "mafed_distill_abi_version", "mafed_distill_error_string", "mafed_distill_ws_bytes",
