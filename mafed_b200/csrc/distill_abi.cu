@@ -279,7 +279,6 @@ int dispatch_typed(PathParams& p, bool vector_ok, int pass, cudaStream_t st) {
       // 16 consumer warps: two stages are drained concurrently when a stage holds <= 8 rows (+2.6 % on the
       // 1B shape, neutral elsewhere; profiles/r01_call4_sweep_extra.json)
       const int ncw = g_tune[kTuneTmaWarps].load();
-      if (ncw == 4) return launch_tma<T, LOSS, 4>(p, geo, pass, st);
       if (ncw == 8) return launch_tma<T, LOSS, 8>(p, geo, pass, st);
       return launch_tma<T, LOSS, 16>(p, geo, pass, st);
     }

@@ -67,7 +67,7 @@ def main():
         units = B * (256 + txt) * n_sel
         points = [(0, 0, 0, 0)]   # library default
         for gridmul in (1, 2, 3, 4):
-            for ncw in (4, 8, 16):
+            for ncw in (8, 16):   # (a 4-warp build was tried in profiles/r01b_sweep_ring_box*.json and dropped)
                 if gridmul * (ncw + 1) * 32 > 1184:   # registers: ~90 per thread
                     continue
                 for rows in (1, 2, 4, 8, 16):
