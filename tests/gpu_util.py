@@ -1,6 +1,4 @@
 """Helpers for the -m gpu parity tests: drive the product API exactly as the reference's callers do."""
-import ctypes
-
 import torch
 
 from mafed_b200 import cabi

@@ -3,7 +3,6 @@ wrapper combines per-rank partial sums + counts; finalising them reproduces the 
 import os
 import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

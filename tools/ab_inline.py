@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B: one-pass step with the scale table derived in-kernel vs a separate prologue launch."""
-import ctypes, json, os, sys, time
+import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
