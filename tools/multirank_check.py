@@ -126,6 +126,14 @@ def graph_replay_check(rank, world):
         ok &= good(out, ref)
     eager = step()                      # eager steps after replays: the device-side epochs simply go on
     ok &= good(eager, ref)
+    # a rank that arrives late (data loader hiccup, checkpoint write): the peers' kernels wait for it inside the
+    # spin bound (60 s by default) and the step is still exact
+    import time
+    torch.cuda.synchronize()
+    if rank == world - 1:
+        time.sleep(3.0)
+    late = step()
+    ok &= good(late, ref)
     print(f"rank {rank}: CUDA-graph replay of the sharded step {'OK' if ok else 'FAIL'}", flush=True)
     return ok
 
