@@ -69,10 +69,11 @@ def _check(case, z, tag, loss, layer_losses, grads):
     assert all(grads[l] is None for l in range(nh, case["n_tuple"]))   # the reference leaves the tail untouched
 
 
-@pytest.mark.parametrize("tag", ["ragged", "ones"])
-def test_oracle_matches_reference_at_config0(tag):
+@pytest.mark.parametrize("name,tag", [("C1", "ragged"), ("C1", "ones"), ("C2", "ragged")])
+def test_oracle_matches_reference_at_full_size(name, tag):
+    """The CPU restatement against the unmodified reference at configs[0] (fp32) and configs[1] (bf16 autocast)."""
     from golden_util import oracle_cfg
-    case, z = CONFIGS["C1"], _golden("C1")
+    case, z = CONFIGS[name], _golden(name)
     st, te, am = _inputs(case, z, tag)
     ref = O.forward_backward(st, te, am, oracle_cfg(case))
     _check(case, z, tag, ref["loss"], dict(ref["layer_losses"]), ref["grads"])
