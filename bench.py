@@ -326,7 +326,6 @@ def main():
     if world > 1:
         dist.barrier()
     lib = cabi.load()
-    lib.mafed_distill_set_variant({"default": 0, "ldg": 1, "tma": 2}[args.variant])
     from mafed_b200.distill_op import distill_backward, distill_forward
 
     wl = args.workload
@@ -373,7 +372,7 @@ def main():
         out, scale, ln = distill_fused(st, te, grads, am, plan, group=None)  # the whole step: one launch
         if ev:
             ev[1].record()
-        distill_backward(ln, grads, scale, gout, skip_if_equals=plan.assumed_grad_out)  # fix-up: returns at once
+        distill_backward(ln, grads, scale, gout, skip_if_equals=plan.assumed_grad_out)  # the gate: returns at once
         if ev:
             ev[2].record()
         return out

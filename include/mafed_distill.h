@@ -20,13 +20,17 @@
  *     on `stream` and is CUDA-graph capturable.
  *
  * Two ways to run a step (both produce the reference's loss and gradients):
- *   two-pass : mafed_distill_fwd -> mafed_distill_epilogue -> ... -> mafed_distill_bwd
- *              (5*D*e bytes of HBM traffic per token*layer)
- *   one-pass : mafed_distill_prologue -> mafed_distill_fused -> mafed_distill_epilogue(losses only)
- *              -> ... -> mafed_distill_bwd(fix-up, returns at once when the upstream gradient is
- *              the one assumed)                      (3*D*e bytes per token*layer)
- * Across batch shards (one process per GPU): mafed_distill_reduce -> allreduce(sums) ->
- * mafed_distill_finalize replace the epilogue; the one-pass step first allreduces the two counts.
+ *   one-pass : mafed_distill_step -- ONE kernel launch: modality masks, gradient scale, loss sums AND gradients from
+ *              a single read of student and teacher, losses (3*D*e bytes of HBM traffic per token*layer) -- and, in
+ *              the backward of the autograd graph, mafed_distill_bwd(skip_if_equals): a 1-CTA gate that returns at
+ *              once when the upstream gradient is the one assumed and otherwise starts the exact backward itself.
+ *   two-pass : mafed_distill_fwd_step (forward + losses + scale table, one launch) ... mafed_distill_bwd
+ *              (5*D*e bytes per token*layer).
+ * Across batch shards (one process per GPU) both forms take a peer-memory communicator (mafed_comm_*) and stay one
+ * launch; without one the stages are available separately for an NCCL sequence:
+ * mafed_distill_fwd | mafed_distill_fused -> mafed_distill_scalar_stage(REDUCE|COUNTS) -> allreduce(sums) ->
+ * mafed_distill_scalar_stage(LOSSES|SCALE).
+ * The library keeps no process-global mutable state: experiment knobs travel with the call (mafed_shape_t::tuning).
  */
 #ifndef MAFED_DISTILL_H_
 #define MAFED_DISTILL_H_
@@ -38,7 +42,7 @@
 extern "C" {
 #endif
 
-#define MAFED_ABI_VERSION 3
+#define MAFED_ABI_VERSION 4
 #define MAFED_MAX_LAYERS 64
 
 enum { MAFED_F32 = 0, MAFED_BF16 = 1, MAFED_F16 = 2 };
@@ -61,6 +65,12 @@ enum {
 /* flags of mafed_distill_scalar_stage */
 enum { MAFED_STAGE_REDUCE = 1, MAFED_STAGE_COUNTS = 2, MAFED_STAGE_LOSSES = 4, MAFED_STAGE_SCALE = 8 };
 
+/* Experiment knobs of ONE call (benchmarks and A/B measurements; keys in mafed_b200/cabi.py).  All zero = the
+ * library's defaults, which is also what a NULL mafed_shape_t::tuning means. */
+typedef struct mafed_tuning {
+  int32_t v[24];
+} mafed_tuning_t;
+
 /* Geometry of one step.  rows of a layer: N = B*T (or B in CLS mode). */
 typedef struct mafed_shape {
   int32_t n_layers;   /* selected layers in this call, 1..MAFED_MAX_LAYERS */
@@ -71,6 +81,7 @@ typedef struct mafed_shape {
   int32_t dtype;      /* MAFED_F32 | MAFED_BF16 | MAFED_F16 (student, teacher and gradient) */
   int32_t loss_kind;  /* MAFED_LOSS_MSE (distillation.py:237-249) | MAFED_LOSS_COSINE (:226-235) */
   int32_t cls;        /* 1: CLS distillation (distillation.py:126-132,251-257) */
+  const mafed_tuning_t* tuning;   /* NULL: defaults */
 } mafed_shape_t;
 
 /* Host-side weight tables (distillation.py:110-113,163; distillation_loss_weights.py:49-60). */
@@ -91,74 +102,13 @@ int mafed_distill_sums_len(int n_layers);
 /* Length (in floats) of the `out` vector: total, n_layers layer losses, 2*n_layers modality losses. */
 int mafed_distill_out_len(int n_layers);
 
-/* Fused forward over all selected layers: one pass over student and teacher
- * (replaces the 2 x _compute_{mse,cosine}_distillation_loss passes per layer,
- * distillation.py:152-162,226-249).  Writes per-CTA partial [layer][text|vision] sums to `ws`. */
-int mafed_distill_fwd(const mafed_shape_t* shape, const void* const* student_ptrs,
-                      const void* const* teacher_ptrs, const int64_t* attn_mask, void* ws, void* stream);
-
-/* The single-CTA scalar stage; `flags` selects its parts (MAFED_STAGE_*):
- *   REDUCE : deterministic fp64 reduction of `ws` (fixed order) -> sums[0 .. 2L)
- *   COUNTS : n_text = sum(attn_mask), n_vis = B*n_vis           -> sums[2L], sums[2L+1]
- *   LOSSES : sums -> out[1+3L] = {total, layer losses, (text, vision) losses}
- *            (distillation.py:110-120,163; distillation_loss_weights.py:148-174)
- *   SCALE  : counts -> bwd_scale[2L] = c_l * coeff * w_m * k / n_m  (k = 2/D for mse, 1 for cosine)
- * Parts that are not selected read their inputs from `sums`; parts that are write them there
- * (when `sums` is not NULL).  The helpers below are the four combinations the path uses. */
-int mafed_distill_scalar_stage(const mafed_shape_t* shape, const mafed_weights_t* weights, int flags,
-                               const int64_t* attn_mask, const void* ws, double* sums, float* out,
-                               float* bwd_scale, void* stream);
-
-/* REDUCE|COUNTS: the rank-local vector the single NCCL allreduce combines across batch shards. */
-int mafed_distill_reduce(const mafed_shape_t* shape, const int64_t* attn_mask, const void* ws,
-                         double* sums, void* stream);
-/* LOSSES|SCALE from (global) sums. */
-int mafed_distill_finalize(const mafed_shape_t* shape, const mafed_weights_t* weights, const double* sums,
-                           float* out, float* bwd_scale, void* stream);
-/* REDUCE|COUNTS|LOSSES|SCALE in one launch (single-GPU two-pass step); bwd_scale may be NULL
- * (-> no SCALE, the one-pass step's epilogue). */
-int mafed_distill_epilogue(const mafed_shape_t* shape, const mafed_weights_t* weights,
-                           const int64_t* attn_mask, const void* ws, double* sums, float* out,
-                           float* bwd_scale, void* stream);
-/* COUNTS|SCALE before a one-pass step.  If `global_counts` is not NULL, COUNTS is skipped and
- * global_counts[2L], [2L+1] (already allreduced) are used. */
-int mafed_distill_prologue(const mafed_shape_t* shape, const mafed_weights_t* weights,
-                           const int64_t* attn_mask, double* global_counts, double* sums, float* bwd_scale,
-                           void* stream);
-
-/* Fused backward: grad[l][row] = grad_out * bwd_scale[l][m(row)] * w(row) * d f(h,p)/dh, zero for
- * padded text rows; one pass, 2 reads + 1 write (replaces autograd's per-layer, per-modality chains
- * of distillation.py:226-249).  `grad_out` is a DEVICE float scalar (NULL = 1.0).  A NULL entry in
- * grad_ptrs skips that layer.  If `skip_if_equals` is not NULL (a HOST float), the launch is a
- * fix-up after mafed_distill_fused: the kernel returns at once when *grad_out == *skip_if_equals. */
-int mafed_distill_bwd(const mafed_shape_t* shape, const void* const* student_ptrs,
-                      const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
-                      const float* bwd_scale, const float* grad_out, const float* skip_if_equals,
-                      void* stream);
-
-/* One-pass step: loss sums AND gradients from a single read of student and teacher.  The gradient
- * scale depends only on the token counts and the host weight tables (not on the loss), so it is
- * known before the pass; the upstream gradient is assumed to be `assumed_grad_out` (1/accumulate_
- * grad_batches under Lightning, vqa_cont_learner.py:213-236) and checked later by
- * mafed_distill_bwd(..., skip_if_equals).  A NULL entry in grad_ptrs still contributes to the sums.
- * `weights` != NULL (single-rank step): the call also produces `bwd_scale` -- for masks of <= 16 Ki
- * entries every CTA of the kernel derives the table itself while its first tiles are in flight (no
- * prologue launch), otherwise a prologue is launched first.  `weights` == NULL: `bwd_scale` is an input
- * (mafed_distill_prologue with the allreduced counts, batch-sharded step). */
-int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_ptrs,
-                        const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
-                        const mafed_weights_t* weights, float* bwd_scale, float assumed_grad_out, void* ws,
-                        void* stream);
-
-/* ---- batch-sharded step without NCCL on the critical path: peer-memory communicator ----------------
- * One process per GPU of one NVLink/NVSwitch box.  Each rank creates a small mailbox (cudaMalloc +
- * CUDA IPC handle), the handles are exchanged out of band (torch.distributed all_gather in
- * mafed_b200/comm.py) and every rank maps its peers' mailboxes.  mafed_distill_scalar_stage_comm is
- * mafed_distill_scalar_stage with a one-shot SUM-allreduce of the selected part of the sums vector
- * (MAFED_COMM_SUMS: [0, 2L), MAFED_COMM_COUNTS: [2L, 2L+2)) performed inside the same kernel with NVLink
- * peer stores of self-validating words (value halves tagged with the epoch; no fence, no flag), after
- * REDUCE/COUNTS and before LOSSES/SCALE.  Results are bit-identical on all
- * ranks; spins are bounded (mafed_comm_set_timeout; mafed_comm_status reports a timeout), `sums` must not be NULL. */
+/* ---- peer-memory communicator: the batch-sharded step without NCCL on the critical path -----------------
+ * One process per GPU of one NVLink/NVSwitch box.  Each rank creates a small mailbox (cudaMalloc + CUDA IPC
+ * handle), the handles are exchanged out of band (torch.distributed all_gather in mafed_b200/comm.py) and every
+ * rank maps its peers' mailboxes.  Exchanges are one-shot SUM-allreduces of <= 2L+2 doubles performed INSIDE the
+ * path's kernels with NVLink peer stores of self-validating words (value halves tagged with the epoch; no fence,
+ * no flag); results are bit-identical on all ranks; the epochs live on the device (CUDA-graph replayable); spins
+ * are bounded (mafed_comm_set_timeout; a timeout sets the status and yields NaN). */
 typedef struct mafed_comm mafed_comm_t;
 enum { MAFED_COMM_SUMS = 1, MAFED_COMM_COUNTS = 2 };
 int mafed_comm_handle_bytes(void);
@@ -168,48 +118,93 @@ int mafed_comm_connect(mafed_comm_t* comm, const void* all_handles /* world x ha
 /* Spin bound of one in-kernel wait (default 60 s, or MAFED_B200_COMM_TIMEOUT_S at creation).  A wait that runs
  * into it sets the status and yields NaN: the step's loss and gradients come out NaN instead of silently wrong. */
 int mafed_comm_set_timeout(mafed_comm_t* comm, double seconds);
+/* The status word lives in mapped pinned host memory (the kernels store into it on a timeout): this is a plain
+ * host read that never synchronises.  It reflects every exchange of the kernels that have finished. */
 int mafed_comm_status(mafed_comm_t* comm, int* status_out /* 0 ok, 1 a peer timed out */);
 /* SM-cycle totals since creation (synchronises the device): [0] in-kernel counts exchange as seen by CTA 0,
  * [1] own peer stores of a sums exchange, [2] waiting for the peers' vectors, [3] sums exchanges. */
 int mafed_comm_trace(mafed_comm_t* comm, unsigned long long* out4);
 int mafed_comm_destroy(mafed_comm_t* comm);
-int mafed_distill_scalar_stage_comm(const mafed_shape_t* shape, const mafed_weights_t* weights, int flags,
-                                    const int64_t* attn_mask, const void* ws, double* sums, float* out,
-                                    float* bwd_scale, mafed_comm_t* comm, int comm_what, void* stream);
 
-/* mafed_distill_fused for the batch-sharded step: with `comm` (and `weights`) the exchange of the two token
- * counts happens INSIDE the fused kernel -- CTA 0 fires this rank's counts into every peer mailbox, all CTAs poll
- * the local mailbox and derive the scale table -- so the step needs no prologue launch and the NVLink trip hides
- * behind the first tiles.  The epoch of the exchange is the device-side counter + 1, read by every CTA at its
- * start and advanced by the last CTA to finish, so the call is CUDA-graph replayable.  comm == NULL behaves like
- * mafed_distill_fused. */
-int mafed_distill_fused_comm(const mafed_shape_t* shape, const void* const* student_ptrs,
-                             const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
-                             const mafed_weights_t* weights, float* bwd_scale, float assumed_grad_out, void* ws,
-                             mafed_comm_t* comm, void* stream);
+/* Token counts ahead of the step.  The counts depend only on the attention mask, which is known when the memory
+ * batch is drawn -- before the student forward (distillation.py:85-91).  This 1-CTA launch sums the mask, writes
+ * {n_text, n_vis rows} of this rank into every peer's mailbox (fire and forget, no wait) and leaves a ticket
+ * (int64[4]: exchange epoch, then this rank's two counts as doubles) in `ticket`.  A later mafed_distill_step given the same ticket reads
+ * finished global counts from its own mailbox instead of exchanging them at its start.  Up to 3 prefetched
+ * batches may be outstanding.  comm == NULL (single rank): only the local counts are left in the ticket. */
+int mafed_distill_prefetch_counts(const mafed_shape_t* shape, const int64_t* attn_mask, mafed_comm_t* comm,
+                                  int64_t* ticket, void* stream);
 
-/* ---- the whole step as ONE call (what mafed_b200/distill_op.py uses) -------------------------------------
- * mafed_distill_step = [mafed_distill_modality_masks] + mafed_distill_fused(_comm) + the LOSSES stage, i.e. all of
- * FeatureDistillation.distill (distillation.py:105-166) plus the backward of its autograd graph.  For shapes the
- * TMA-ring kernel takes (rows <= 32 KB, 16-byte aligned) and masks of <= 16 Ki entries it is ONE kernel launch:
- * every CTA derives the gradient scale itself, all CTAs together write the two modality masks, and the CTA that
- * finishes LAST reduces the per-CTA partial sums in fixed order (bit-reproducible) and forms the losses -- with a
- * communicator it also exchanges the 2L sums with the peers there.  Other shapes run the same step as the
- * separate launches above.  out[1+3L] as in LOSSES; bwd_scale[2L] is written for the later fix-up
- * (mafed_distill_bwd with skip_if_equals); sums (optional single-rank, required with comm) receives the global
- * [2L+2] vector; lang_mask / image_mask (both or neither, int64 [B, T]) are optional.  All exchange epochs live
- * on the device: the sharded forms are CUDA-graph replayable too.
- * mafed_distill_fwd_step is the two-pass form's first half: mafed_distill_fwd + REDUCE|COUNTS|LOSSES|SCALE in
- * one launch (sharded: sums and counts exchanged in the tail). */
+/* ---- the whole step as ONE call (what mafed_b200 uses) ----------------------------------------------------
+ * mafed_distill_step = all of FeatureDistillation.distill (distillation.py:105-166) plus the backward of its
+ * autograd graph: modality masks, counts -> gradient scale, loss sums + gradients from a single read of student and
+ * teacher, losses.  The gradient scale depends only on the token counts and the host weight tables (not on the
+ * loss), so it is known before the pass; the upstream gradient is assumed to be `assumed_grad_out` (1/accumulate_
+ * grad_batches under Lightning, vqa_cont_learner.py:213-236) and checked later by mafed_distill_bwd(skip_if_equals).
+ * For shapes the TMA-ring kernel takes (rows <= 32 KB, 16-byte aligned) and masks of <= 16 Ki entries it is ONE
+ * kernel launch: every CTA derives the gradient scale itself, all CTAs together write the two modality masks, and
+ * the CTA that finishes LAST reduces the per-CTA partial sums in fixed order (bit-reproducible) and forms the
+ * losses.  With a communicator the counts are exchanged inside the kernel behind its first tiles -- or, with a
+ * `counts_ticket` from mafed_distill_prefetch_counts, simply read from the own mailbox, where they landed long ago
+ * -- and the last CTA exchanges the 2L sums with the peers.  Other shapes run the same step as separate launches.
+ * out[1+3L] = {total, layer losses, (text, vision) losses}; bwd_scale[2L] is written for the later gate; sums
+ * (optional single-rank, required with comm) receives the global [2L+2] vector; lang_mask / image_mask (both or
+ * neither, int64 [B, T]) are optional; a NULL entry in grad_ptrs still contributes to the sums. */
 int mafed_distill_step(const mafed_shape_t* shape, const void* const* student_ptrs,
                        const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
                        const mafed_weights_t* weights, float assumed_grad_out, void* ws, float* out,
                        float* bwd_scale, double* sums, int64_t* lang_mask, int64_t* image_mask,
-                       mafed_comm_t* comm, void* stream);
+                       mafed_comm_t* comm, const int64_t* counts_ticket, void* stream);
+/* The two-pass form's first half: fused forward + REDUCE|COUNTS|LOSSES|SCALE in one launch (sharded: sums and
+ * counts exchanged in the tail). */
 int mafed_distill_fwd_step(const mafed_shape_t* shape, const void* const* student_ptrs,
                            const void* const* teacher_ptrs, const int64_t* attn_mask,
                            const mafed_weights_t* weights, void* ws, float* out, float* bwd_scale, double* sums,
                            mafed_comm_t* comm, void* stream);
+
+/* Fused backward: grad[l][row] = g * bwd_scale[l][m(row)] * w(row) * d f(h,p)/dh with g = *grad_out *
+ * grad_out_scale, zero for padded text rows; one pass, 2 reads + 1 write (replaces autograd's per-layer,
+ * per-modality chains of distillation.py:226-249).  `grad_out` is a DEVICE float scalar (NULL = 1.0),
+ * `grad_out_scale` a host factor (e.g. world_size to undo DDP's gradient averaging).  A NULL entry in grad_ptrs
+ * skips that layer.  If `skip_if_equals` is not NULL (a HOST float) the call is the one-pass step's gate: a 1-CTA
+ * launch compares g with *skip_if_equals on the device and returns at once when they match (the gradients of
+ * mafed_distill_step are already right); otherwise it starts the backward itself, stream-ordered behind it
+ * (device-side tail launch).  `grad_out_seen` (optional, device-accessible, e.g. pinned host memory) receives g,
+ * so that a caller can learn the upstream gradient its steps really get without synchronising. */
+int mafed_distill_bwd(const mafed_shape_t* shape, const void* const* student_ptrs,
+                      const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
+                      const float* bwd_scale, const float* grad_out, float grad_out_scale,
+                      const float* skip_if_equals, float* grad_out_seen, void* stream);
+
+/* ---- the stages separately (NCCL sequence, tests) -------------------------------------------------------------
+ * Fused forward over all selected layers: one pass over student and teacher (replaces the 2 x
+ * _compute_{mse,cosine}_distillation_loss passes per layer, distillation.py:152-162,226-249).  Writes per-CTA
+ * partial [layer][text|vision] sums to `ws`. */
+int mafed_distill_fwd(const mafed_shape_t* shape, const void* const* student_ptrs,
+                      const void* const* teacher_ptrs, const int64_t* attn_mask, void* ws, void* stream);
+
+/* The streaming kernel of the one-pass step alone: gradients + per-CTA partial sums (no losses).  `weights` != NULL:
+ * the call also produces `bwd_scale` from the mask counts (with `comm`, from the counts exchanged inside the
+ * kernel); `weights` == NULL: `bwd_scale` is an input (SCALE stage run on allreduced counts). */
+int mafed_distill_fused(const mafed_shape_t* shape, const void* const* student_ptrs,
+                        const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
+                        const mafed_weights_t* weights, float* bwd_scale, float assumed_grad_out, void* ws,
+                        mafed_comm_t* comm, void* stream);
+
+/* The single-CTA scalar stage; `flags` selects its parts (MAFED_STAGE_*):
+ *   REDUCE : deterministic fp64 reduction of `ws` (fixed order) -> sums[0 .. 2L)
+ *   COUNTS : n_text = sum(attn_mask), n_vis = B*n_vis           -> sums[2L], sums[2L+1]
+ *   LOSSES : sums -> out[1+3L] = {total, layer losses, (text, vision) losses}
+ *            (distillation.py:110-120,163; distillation_loss_weights.py:148-174)
+ *   SCALE  : counts -> bwd_scale[2L] = c_l * coeff * w_m * k / n_m  (k = 2/D for mse, 1 for cosine)
+ * Parts that are not selected read their inputs from `sums`; parts that are write them there (when `sums` is not
+ * NULL).  With `comm` the selected part of the sums vector (`comm_what`: MAFED_COMM_SUMS = [0, 2L),
+ * MAFED_COMM_COUNTS = [2L, 2L+2)) is allreduced over the peer mailboxes after REDUCE/COUNTS and before
+ * LOSSES/SCALE (`sums` must then not be NULL).  The usual combinations: REDUCE|COUNTS (rank-local vector before an
+ * allreduce), LOSSES|SCALE (after it), COUNTS|SCALE (before mafed_distill_fused with weights == NULL). */
+int mafed_distill_scalar_stage(const mafed_shape_t* shape, const mafed_weights_t* weights, int flags,
+                               const int64_t* attn_mask, const void* ws, double* sums, float* out,
+                               float* bwd_scale, mafed_comm_t* comm, int comm_what, void* stream);
 
 /* Gradient-norm modality importances (distillation_loss_weights.py:122-137): for every tensor of the
  * table (one per selected layer, [B, T, D]) the per-token L2 norm over D (`torch.linalg.norm(grad,
@@ -242,12 +237,6 @@ int mafed_host_step_run(mafed_host_step_t* step, const mafed_weights_t* weights,
 int mafed_host_step_destroy(mafed_host_step_t* step);
 int mafed_host_register(void* ptr, size_t bytes);
 int mafed_host_unregister(void* ptr);
-
-/* Experiment knobs (benchmarks only; process-global): kernel family for the next calls
- * (0 = default, 1 = ldg: register-staged 128-bit loads, 2 = tma: cp.async.bulk + mbarrier ring),
- * and integer tuning keys (see mafed_b200/cabi.py). */
-int mafed_distill_set_variant(int variant);
-int mafed_distill_set_tuning(int key, int value);
 
 #ifdef __cplusplus
 }

@@ -19,16 +19,30 @@
 #pragma once
 #include "distill_common.cuh"
 
-namespace mafed {
+namespace MAFED_NS {
 
 constexpr size_t kCommDataBytes = sizeof(unsigned long long) * 2 * 2 * kCommMaxRanks * kCommSlots;
-constexpr size_t kCommMailboxBytes = kCommDataBytes + 64;  // + epoch, status, trace
+// Second region: token counts sent AHEAD of the step (mafed_distill_prefetch_counts).  They have their own epoch
+// counter and kCommCountSlots generations, so a rank may prefetch the counts of up to kCommCountSlots - 1 batches
+// before the step that consumes the first of them (the sums exchange of every step keeps the ranks within one
+// step of each other):
+//   cnt [kCommCountSlots][world][2 values][2 words] uint64 -- slot [e % kCommCountSlots][r] is written only by rank r
+constexpr int kCommCountSlots = 4;
+constexpr size_t kCommCountsBytes = sizeof(unsigned long long) * kCommCountSlots * kCommMaxRanks * 2 * 2;
+// tail of the mailbox: +0 epoch, +8 counts epoch, +16 (unused), +32 trace[4]
+constexpr size_t kCommTailAt = kCommDataBytes + kCommCountsBytes;
+constexpr size_t kCommMailboxBytes = kCommTailAt + 64;
 
 __device__ __forceinline__ uint32_t ll_tag(unsigned long long epoch) { return (uint32_t)epoch | 0x80000000u; }
 
 // Word pair of slot k of rank r's vector in a mailbox.
 __device__ __forceinline__ unsigned long long* ll_slot(unsigned long long* mailbox, int parity, int r, int k) {
   return mailbox + (((size_t)parity * kCommMaxRanks + r) * kCommSlots + k) * 2;
+}
+
+// Word pair of count k (0 text, 1 vision rows) of rank r, generation `gen`, in a mailbox.
+__device__ __forceinline__ unsigned long long* ll_count_slot(unsigned long long* mailbox, int gen, int r, int k) {
+  return mailbox + kCommDataBytes / sizeof(unsigned long long) + (((size_t)gen * kCommMaxRanks + r) * 2 + k) * 2;
 }
 
 __device__ __forceinline__ void ll_store(unsigned long long* slot, double v, uint32_t tag) {
@@ -106,4 +120,4 @@ __device__ __forceinline__ void peer_allreduce(const CommDev& c, double* vals, i
   }
 }
 
-}  // namespace mafed
+}  // namespace MAFED_NS

@@ -7,7 +7,13 @@
 
 #include "mafed_distill.h"
 
-namespace mafed {
+// The kernels live in `mafed`; the relocatable-device-code unit that holds the gated backward (distill_gate.cu)
+// compiles the same headers into `mafed_gate`, so that the two units never share a kernel symbol.
+#ifndef MAFED_NS
+#define MAFED_NS mafed
+#endif
+
+namespace MAFED_NS {
 
 constexpr int kMaxLayers = MAFED_MAX_LAYERS;
 // Third "loss": per-token L2 norm of a single tensor (no teacher), for the gradient-norm modality
@@ -28,7 +34,8 @@ constexpr double kCommDefaultTimeoutS = 60.0;  // spin bound of an exchange (MAF
 struct CommDev {
   unsigned long long* ll[kCommMaxRanks];    // mailbox of every rank (peer-mapped; [rank] is local), see distill_comm.cuh
   unsigned long long* epoch;                // local: collectives issued so far
-  int* status;                              // local: 0 ok, 1 timeout
+  unsigned long long* epoch_counts;         // local: count prefetches issued so far
+  int* status;                              // 0 ok, 1 timeout; mapped pinned HOST memory (the host reads it without a sync)
   unsigned long long* trace;                // local: SM-cycle totals [counts exchange, publish, wait for peers, calls]
   long long timeout_cycles;                 // spin bound of one wait, in SM cycles
   int world;                                // 0 = no communicator (single rank)
@@ -54,6 +61,7 @@ struct PathParams {
   int n_chunks;                  // 16-byte chunks per row (vector kernels)
   int reverse;                   // backward: walk work items last-to-first (L2 reuse after forward)
   float fixed_gout;              // fused pass: upstream gradient assumed at forward time (host value)
+  float gout_scale;              // backward: host factor on *grad_out (e.g. world_size to undo DDP's averaging)
   int skip_if_gout_equals;       // backward fix-up: return at once when *grad_out == fixed_gout
   int single_input;              // 1: only `s` is read (token-norm sums); the teacher table is ignored
   // one-pass step with the prologue folded in: every CTA derives the scale table from the mask itself
@@ -67,6 +75,7 @@ struct PathParams {
   // reads the device-side epoch counter at its start; only the LAST CTA to finish (tail) advances it, so all
   // CTAs of a launch agree on the epoch and the sequence stays CUDA-graph replayable.
   int comm_counts;               // 1: exchange the counts in this kernel (epoch = device-side counter + 1)
+  const long long* counts_ticket;  // counts sent ahead of the step (k_prefetch_counts): {epoch, bits(n_text), bits(n_vis rows)}
   CommDev comm;
   int load_policy;               // L2 eviction hint for student/teacher reads (CachePolicy)
   int store_policy;              // L2 eviction hint for gradient writes
@@ -313,4 +322,4 @@ __device__ __forceinline__ void cta_sums_store(const CtaSums<WARPS>& s, float* w
   }
 }
 
-}  // namespace mafed
+}  // namespace MAFED_NS

@@ -9,7 +9,7 @@
 #include "distill_comm.cuh"
 #include "distill_common.cuh"
 
-namespace mafed {
+namespace MAFED_NS {
 
 constexpr int kEpiThreads = 1024;
 
@@ -144,6 +144,51 @@ __device__ __forceinline__ void scalar_stage(const EpiArgs& p, const CommDev& co
   }
 }
 
+// Token counts ahead of the step (mafed_distill_prefetch_counts): one CTA sums the attention mask, takes the next
+// value of the prefetch epoch counter, fires {n_text, n_vis rows} of this rank into every rank's mailbox (no wait)
+// and leaves the ticket {epoch, bits(n_text), bits(n_vis rows)} for the step that will consume the counts.
+struct PrefetchParams {
+  const int64_t* mask;
+  long long n_mask;
+  double n_vis_rows;
+  long long* ticket;   // [4]
+  CommDev comm;
+};
+
+__global__ void __launch_bounds__(kEpiThreads) k_prefetch_counts(const __grid_constant__ PrefetchParams p) {
+  __shared__ long long s_cnt[kEpiThreads / 32];
+  __shared__ double s_vals[2];
+  __shared__ unsigned long long s_epoch;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long c = 0;
+  for (long long i = tid; i < p.n_mask; i += kEpiThreads) c += p.mask[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) s_cnt[warp] = c;
+  __syncthreads();
+  if (tid == 0) {
+    long long tot = 0;
+    for (int i = 0; i < kEpiThreads / 32; ++i) tot += s_cnt[i];
+    s_vals[0] = (double)tot;
+    s_vals[1] = p.n_vis_rows;
+    unsigned long long e = 0ull;
+    if (p.comm.world > 1) e = ++(*p.comm.epoch_counts);
+    s_epoch = e;
+    p.ticket[0] = (long long)e;
+    p.ticket[1] = __double_as_longlong(s_vals[0]);
+    p.ticket[2] = __double_as_longlong(s_vals[1]);
+    p.ticket[3] = 0;
+  }
+  __syncthreads();
+  if (p.comm.world > 1 && tid < 2 * p.comm.world) {
+    const int peer = tid >> 1, k = tid & 1;
+    const unsigned long long e = s_epoch;
+    ll_store(ll_count_slot(p.comm.ll[peer], (int)(e % kCommCountSlots), p.comm.rank, k), s_vals[k], ll_tag(e));
+  }
+}
+
 __global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant__ EpiParams p) {
   __shared__ EpiSmem sm;
   pdl_wait();
@@ -151,4 +196,4 @@ __global__ void __launch_bounds__(kEpiThreads) k_epilogue(const __grid_constant_
   scalar_stage<kEpiThreads>(p.a, p.comm, p.w, sm, (int)threadIdx.x, SyncCta());
 }
 
-}  // namespace mafed
+}  // namespace MAFED_NS

@@ -4,7 +4,7 @@
 #pragma once
 #include "distill_common.cuh"
 
-namespace mafed {
+namespace MAFED_NS {
 
 constexpr int kLdgThreads = 256;
 constexpr int kLdgWarps = kLdgThreads / 32;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void grad_elems(const float (&a)[NE], const float (&b
 template <int MODE>
 __device__ __forceinline__ bool upstream_grad(const PathParams& p, float& gout) {
   if (MODE == kFused) { gout = p.fixed_gout; return true; }
-  gout = p.grad_out ? __ldg(p.grad_out) : 1.f;
+  gout = (p.grad_out ? __ldg(p.grad_out) : 1.f) * p.gout_scale;
   return !(p.skip_if_gout_equals && gout == p.fixed_gout);
 }
 
@@ -360,4 +360,4 @@ __global__ void __launch_bounds__(kLdgThreads) k_bwd_generic(const __grid_consta
   }
 }
 
-}  // namespace mafed
+}  // namespace MAFED_NS

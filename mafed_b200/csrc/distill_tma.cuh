@@ -7,7 +7,7 @@
 #include "distill_common.cuh"
 #include "distill_epilogue.cuh"
 
-namespace mafed {
+namespace MAFED_NS {
 
 constexpr int kTmaMaxStages = 8;
 constexpr int kTmaMaxRows = 32;  // rows per stage (one per producer lane)
@@ -309,7 +309,7 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
   if (FUSED) {
     gout = p.fixed_gout;
   } else {
-    gout = p.grad_out ? __ldg(p.grad_out) : 1.f;
+    gout = (p.grad_out ? __ldg(p.grad_out) : 1.f) * p.gout_scale;
     if (p.skip_if_gout_equals && gout == p.fixed_gout) return;  // fix-up launch with nothing to fix
   }
   if (warp == NCW) {
@@ -335,46 +335,76 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
   }
   if (FUSED && p.inline_scale) {
     __shared__ long long s_cnt[NCW];
-    long long c = 0;
-    for (long long i = threadIdx.x; i < p.n_mask; i += NCW * 32) c += p.mask[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) s_cnt[warp] = c;
-    named_bar_sync(1, NCW * 32);
-    long long n_text_local = 0;
-#pragma unroll
-    for (int i = 0; i < NCW; ++i) n_text_local += s_cnt[i];
-    double n_text = (double)n_text_local, n_vis_rows = p.n_vis_rows;
-    if (p.comm.world > 1 && p.comm_counts) {
-      // Batch-sharded step: the two token counts are exchanged right here.  CTA 0 fires this rank's counts into
-      // every rank's mailbox as self-validating words (distill_comm.cuh: no fence, no flag); every CTA then polls
-      // its OWN rank's mailbox (local L2) for all peers and sums in rank order.  The one-way NVLink trip hides
-      // behind the first tiles.
-      const CommDev& c = p.comm;
-      const long long t_x0 = clock64();
-      // nobody writes the counter before the last CTA's tail: every CTA of this launch reads the same value
-      const unsigned long long e = __ldcg(c.epoch) + 1ull;
-      counts_epoch = e;
-      const int par = (int)(e & 1ull);
-      const uint32_t tag = ll_tag(e);
-      __shared__ double s_peer[kCommMaxRanks][2];
-      if (blockIdx.x == 0) {
+    __shared__ double s_peer[kCommMaxRanks][2];
+    const CommDev& c = p.comm;
+    const bool sharded = c.world > 1 && p.comm_counts;
+    double n_text, n_vis_rows;
+    if (p.counts_ticket != nullptr) {
+      // The counts were computed -- and, across batch shards, sent to every peer -- when the batch was drawn
+      // (k_prefetch_counts), long before this kernel: nothing to sum, and the poll below finds every peer's words
+      // already in the own mailbox (local L2).  The prefetch has its own epoch counter and slot generations, so the
+      // sums exchange in the tail simply takes the next value of the main counter (counts_epoch stays 0).
+      if (sharded) {
+        const unsigned long long e = (unsigned long long)__ldcg(p.counts_ticket);
+        const long long t_x0 = clock64();
         if ((int)threadIdx.x < 2 * c.world) {
-          const int peer = threadIdx.x >> 1, k = threadIdx.x & 1;
-          ll_store(ll_slot(c.ll[peer], par, c.rank, k), k == 0 ? n_text : n_vis_rows, tag);
+          const int r = threadIdx.x >> 1, k = threadIdx.x & 1;
+          s_peer[r][k] = ll_wait(ll_count_slot(c.ll[c.rank], (int)(e % kCommCountSlots), r, k), ll_tag(e), c.status,
+                                 c.timeout_cycles);
         }
+        named_bar_sync(1, NCW * 32);
+        if (blockIdx.x == 0 && threadIdx.x == 0) c.trace[0] += (unsigned long long)(clock64() - t_x0);
+        n_text = 0.0;
+        n_vis_rows = 0.0;
+        for (int r = 0; r < c.world; ++r) {
+          n_text += s_peer[r][0];
+          n_vis_rows += s_peer[r][1];
+        }
+      } else {
+        n_text = __longlong_as_double(__ldcg(p.counts_ticket + 1));
+        n_vis_rows = __longlong_as_double(__ldcg(p.counts_ticket + 2));
       }
-      if ((int)threadIdx.x < 2 * c.world) {
-        const int r = threadIdx.x >> 1, k = threadIdx.x & 1;
-        s_peer[r][k] = ll_wait(ll_slot(c.ll[c.rank], par, r, k), tag, c.status, c.timeout_cycles);
-      }
+    } else {
+      long long cnt = 0;
+      for (long long i = threadIdx.x; i < p.n_mask; i += NCW * 32) cnt += p.mask[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == 0) s_cnt[warp] = cnt;
       named_bar_sync(1, NCW * 32);
-      if (blockIdx.x == 0 && threadIdx.x == 0) c.trace[0] += (unsigned long long)(clock64() - t_x0);
-      n_text = 0.0;
-      n_vis_rows = 0.0;
-      for (int r = 0; r < c.world; ++r) {
-        n_text += s_peer[r][0];
-        n_vis_rows += s_peer[r][1];
+      long long n_text_local = 0;
+#pragma unroll
+      for (int i = 0; i < NCW; ++i) n_text_local += s_cnt[i];
+      n_text = (double)n_text_local;
+      n_vis_rows = p.n_vis_rows;
+      if (sharded) {
+        // Batch-sharded step: the two token counts are exchanged right here.  CTA 0 fires this rank's counts into
+        // every rank's mailbox as self-validating words (distill_comm.cuh: no fence, no flag); every CTA then polls
+        // its OWN rank's mailbox (local L2) for all peers and sums in rank order.  The one-way NVLink trip hides
+        // behind the first tiles.
+        const long long t_x0 = clock64();
+        // nobody writes the counter before the last CTA's tail: every CTA of this launch reads the same value
+        const unsigned long long e = __ldcg(c.epoch) + 1ull;
+        counts_epoch = e;
+        const int par = (int)(e & 1ull);
+        const uint32_t tag = ll_tag(e);
+        if (blockIdx.x == 0) {
+          if ((int)threadIdx.x < 2 * c.world) {
+            const int peer = threadIdx.x >> 1, k = threadIdx.x & 1;
+            ll_store(ll_slot(c.ll[peer], par, c.rank, k), k == 0 ? n_text : n_vis_rows, tag);
+          }
+        }
+        if ((int)threadIdx.x < 2 * c.world) {
+          const int r = threadIdx.x >> 1, k = threadIdx.x & 1;
+          s_peer[r][k] = ll_wait(ll_slot(c.ll[c.rank], par, r, k), tag, c.status, c.timeout_cycles);
+        }
+        named_bar_sync(1, NCW * 32);
+        if (blockIdx.x == 0 && threadIdx.x == 0) c.trace[0] += (unsigned long long)(clock64() - t_x0);
+        n_text = 0.0;
+        n_vis_rows = 0.0;
+        for (int r = 0; r < c.world; ++r) {
+          n_text += s_peer[r][0];
+          n_vis_rows += s_peer[r][1];
+        }
       }
     }
     if (threadIdx.x == 0) { s_counts[0] = n_text; s_counts[1] = n_vis_rows; }
@@ -541,4 +571,4 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
   }
 }
 
-}  // namespace mafed
+}  // namespace MAFED_NS

@@ -16,6 +16,12 @@ Under ``torch.distributed`` with batch sharding, the per-rank ``[2L+2]`` fp64 pa
 are combined by allreduce; the backward needs no collective.  Nothing here
 synchronises the host with the device.
 
+Host side: ``distill_loss`` hands the whole step to the compiled autograd node (``csrc/torch_node.cpp``,
+``mafed_b200.node``) -- pointer tables, workspace and gradient allocation, stream lookup, the launch and the
+backward gate all run in C++.  The ctypes functions below (``distill_forward`` / ``distill_fused`` /
+``distill_backward``) are the same C-ABI calls one at a time: the NCCL sequence, the kernel-level benchmarks and
+the tests use them.
+
 Replaces the per-layer Python loop of ``mafed/methods/distillation.py:105-166`` and the autograd
 chains behind ``:226-249``.
 """
@@ -27,7 +33,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from . import cabi
+from . import cabi, node
 from .comm import get_peer_comm
 
 _DTYPES = {torch.float32: cabi.F32, torch.bfloat16: cabi.BF16, torch.float16: cabi.F16}
@@ -48,6 +54,7 @@ class DistillPlan:
     single_pass: bool = True                # one-pass step when gradients are needed
     assumed_grad_out: float = 1.0           # upstream gradient the one-pass step bakes in
     _weights: Optional[cabi.Weights] = field(default=None, repr=False)
+    _node_plan: object = field(default=None, repr=False)
 
     def weights(self) -> cabi.Weights:
         if self._weights is None:
@@ -57,6 +64,17 @@ class DistillPlan:
                 cabi.MODW_CLS if self.cls else self.modality_kind, self.distill_coeff,
                 self.layer_coeffs, self.lang_weights)
         return self._weights
+
+    def node_plan(self):
+        """The same tables as the compiled node's ``Plan`` (built once per DistillPlan)."""
+        if self._node_plan is None:
+            self._node_plan = node.load().Plan(
+                cabi.MODW_CLS if self.cls else self.modality_kind, float(self.distill_coeff),
+                [float(c) for c in self.layer_coeffs],
+                None if self.lang_weights is None else [float(c) for c in self.lang_weights],
+                self.loss_kind, bool(self.cls), int(self.n_vis), float(self.grad_multiplier), bool(self.single_pass),
+                float(self.assumed_grad_out))
+        return self._node_plan
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -209,8 +227,8 @@ def token_norm_sums(tensors: Sequence[torch.Tensor], attn_mask: torch.Tensor, n_
         sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
         cabi.check(lib.mafed_distill_token_norm_sums(ln.shape_ref, ln.s_ptrs, ln.mask_ptr, ws.data_ptr(), stream),
                    "mafed_distill_token_norm_sums")
-        cabi.check(lib.mafed_distill_reduce(ln.shape_ref, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream),
-                   "mafed_distill_reduce")
+        cabi.check(cabi.reduce_stage(lib, ln.shape_ref, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream),
+                   "mafed_distill_scalar_stage(reduce)")
     return sums
 
 
@@ -252,11 +270,11 @@ def distill_forward(students, teachers, attn_mask, plan: DistillPlan, group=None
             cabi.check(lib.mafed_distill_fwd(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, ln.mask_ptr, ws.data_ptr(), stream),
                        "mafed_distill_fwd")
             sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
-            cabi.check(lib.mafed_distill_reduce(ln.shape_ref, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream),
-                       "mafed_distill_reduce")
+            cabi.check(cabi.reduce_stage(lib, ln.shape_ref, ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream),
+                       "mafed_distill_scalar_stage(reduce)")
             allreduce_sums(sums, pg)
-            cabi.check(lib.mafed_distill_finalize(ln.shape_ref, w, sums.data_ptr(), out.data_ptr(),
-                                                  bwd_scale.data_ptr(), stream), "mafed_distill_finalize")
+            cabi.check(cabi.finalize_stage(lib, ln.shape_ref, w, sums.data_ptr(), out.data_ptr(),
+                                           bwd_scale.data_ptr(), stream), "mafed_distill_scalar_stage(finalize)")
         else:
             # forward + reduce + counts (+ NVLink peer allreduce) + losses + scale: one launch, no NCCL call
             sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev) if peer is not None else None
@@ -268,20 +286,23 @@ def distill_forward(students, teachers, attn_mask, plan: DistillPlan, group=None
 
 
 def distill_backward(ln: _Launch, grads: Sequence[Optional[torch.Tensor]], bwd_scale: torch.Tensor,
-                     grad_out: Optional[torch.Tensor], skip_if_equals: Optional[float] = None):
-    """Fused backward into pre-allocated ``grads`` (``None`` entries are skipped).  With
-    ``skip_if_equals`` the launch is the one-pass step's fix-up: a no-op on the device when the
-    upstream gradient equals that value."""
+                     grad_out: Optional[torch.Tensor], skip_if_equals: Optional[float] = None,
+                     grad_out_scale: float = 1.0, seen: Optional[torch.Tensor] = None):
+    """Fused backward into pre-allocated ``grads`` (``None`` entries are skipped).  With ``skip_if_equals`` the
+    launch is the one-pass step's gate: a 1-CTA kernel that does nothing when the upstream gradient (times
+    ``grad_out_scale``) equals that value and otherwise starts the backward from the device.  ``seen``: optional
+    pinned float tensor that receives the upstream gradient the gate saw."""
     lib = cabi.load()
     g_ptrs = cabi.ptr_array([g.data_ptr() if g is not None else None for g in grads])
     skip = ctypes.byref(ctypes.c_float(skip_if_equals)) if skip_if_equals is not None else None
     with _on_device(ln.device):
         cabi.check(lib.mafed_distill_bwd(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr,
                                          bwd_scale.data_ptr(), grad_out.data_ptr() if grad_out is not None else None,
-                                         skip, _stream_ptr(ln.device)), "mafed_distill_bwd")
+                                         float(grad_out_scale), skip, seen.data_ptr() if seen is not None else None,
+                                         _stream_ptr(ln.device)), "mafed_distill_bwd")
 
 
-def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group=None, mask_out=None):
+def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group=None, mask_out=None, ticket=None):
     """One-pass step: counts -> gradient scale, loss sums + gradients from one read of student and teacher,
     losses -- a single launch of the fused kernel (``mafed_distill_step``); ``mask_out = (lang, image)`` int64
     ``[B, T]`` tensors are filled by the same kernel.  Returns ``(out, bwd_scale, launch)``."""
@@ -306,24 +327,26 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
                 ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr, w, fixed, ws.data_ptr(), out.data_ptr(),
                 bwd_scale.data_ptr(), sums.data_ptr() if sums is not None else None,
                 lang.data_ptr() if lang is not None else None, image.data_ptr() if image is not None else None,
-                peer.handle if peer is not None else None, stream), "mafed_distill_step")
+                peer.handle if peer is not None else None, ticket.data_ptr() if ticket is not None else None, stream),
+                "mafed_distill_step")
             return out, bwd_scale, ln
         if mask_out is not None:
             modality_masks_into(ln.mask, plan.n_vis, *mask_out)
         sums = torch.empty(2 * L + 2, dtype=torch.float64, device=dev)
         # NCCL: counts allreduce -> scale table -> fused pass -> sums allreduce -> losses
         cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_COUNTS, ln.mask_ptr, None,
-                                                  sums.data_ptr(), None, None, stream), "counts")
+                                                  sums.data_ptr(), None, None, None, 0, stream), "counts")
         allreduce_sums(sums[2 * L:], pg)
-        cabi.check(lib.mafed_distill_prologue(ln.shape_ref, w, None, sums.data_ptr(), None, bwd_scale.data_ptr(),
-                                              stream), "mafed_distill_prologue")
+        cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, w, cabi.STAGE_SCALE, None, None, sums.data_ptr(), None,
+                                                  bwd_scale.data_ptr(), None, 0, stream), "scale")
         cabi.check(lib.mafed_distill_fused(ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr, None,
-                                           bwd_scale.data_ptr(), fixed, ws.data_ptr(), stream), "mafed_distill_fused")
+                                           bwd_scale.data_ptr(), fixed, ws.data_ptr(), None, stream),
+                   "mafed_distill_fused")
         cabi.check(lib.mafed_distill_scalar_stage(ln.shape_ref, None, cabi.STAGE_REDUCE, None, ws.data_ptr(),
-                                                  sums.data_ptr(), None, None, stream), "reduce")
+                                                  sums.data_ptr(), None, None, None, 0, stream), "reduce")
         allreduce_sums(sums[: 2 * L], pg)
-        cabi.check(lib.mafed_distill_finalize(ln.shape_ref, w, sums.data_ptr(), out.data_ptr(), None, stream),
-                   "mafed_distill_finalize")
+        cabi.check(cabi.finalize_stage(lib, ln.shape_ref, w, sums.data_ptr(), out.data_ptr(), None, stream),
+                   "mafed_distill_scalar_stage(finalize)")
     return out, bwd_scale, ln
 
 
@@ -344,7 +367,8 @@ def _alloc_grads(students, needs: Sequence[bool], cls: bool):
 
 
 class _DistillFunction(torch.autograd.Function):
-    """Inputs: (plan, attention_mask, group, teachers tuple, mask_out, *students).  The teachers ride in a plain
+    """The step as a Python autograd Function over the ctypes calls: used when the ranks have no peer-memory
+    communicator (NCCL sequence) -- every other step goes through the compiled node (``_node_step``).  Inputs: (plan, attention_mask, group, teachers tuple, mask_out, *students).  The teachers ride in a plain
     tuple: they never need gradients, so autograd does not have to look at them.  ``mask_out``: ``None`` or the
     pre-allocated ``(lang_masks, image_masks)`` pair to fill (``distillation.py:134-144``)."""
 
@@ -379,52 +403,77 @@ class _DistillFunction(torch.autograd.Function):
         g = grad_total
         if g.dtype != torch.float32 or g.device != ln.device:
             g = g.to(device=ln.device, dtype=torch.float32)
-        if plan.grad_multiplier != 1.0:
-            g = g * plan.grad_multiplier
         if not g.is_contiguous():
             g = g.contiguous()
+        mul = float(plan.grad_multiplier)
         if ctx.grads is not None:
             # one-pass step: gradients already exist; fix them up only if the upstream gradient differs
             grads, ctx.grads = ctx.grads, None
-            fixed = float(plan.assumed_grad_out) * float(plan.grad_multiplier)
-            distill_backward(ln, grads, ctx.bwd_scale, g, skip_if_equals=fixed)
+            fixed = float(plan.assumed_grad_out) * mul
+            distill_backward(ln, grads, ctx.bwd_scale, g, skip_if_equals=fixed, grad_out_scale=mul)
         else:
             grads = _alloc_grads(ln.students, ctx.needs, plan.cls)
-            distill_backward(ln, grads, ctx.bwd_scale, g)
+            distill_backward(ln, grads, ctx.bwd_scale, g, grad_out_scale=mul)
         return (None, None, None, None, None, *grads)
 
 
+# Pinned words that receive the upstream gradient a backward gate saw.  The gate stores into its word when it
+# RUNS, which can be after every Python object of the step is gone, so the words are never freed: one pinned
+# allocation per process, slots handed out round-robin (a slot shared by two strategies after 1024 of them can
+# only mislead the `assumed_grad_out` heuristic, never the results -- the gate itself decides on the device).
+_SEEN_POOL = None
+_seen_next = 0
+
+
+def seen_slot() -> torch.Tensor:
+    """A pinned float32[1] view for ``distill_loss(..., seen=...)``."""
+    global _SEEN_POOL, _seen_next
+    if _SEEN_POOL is None:
+        _SEEN_POOL = torch.zeros(1024, dtype=torch.float32).pin_memory()
+    i = _seen_next % 1024
+    _seen_next += 1
+    slot = _SEEN_POOL[i:i + 1]
+    slot.zero_()
+    return slot
+
+
+def _step(plan: DistillPlan, attn_mask, group, teachers, mask_out, students, ticket=None, seen=None):
+    """One launch-sized step (<= MAX_LAYERS layers): the compiled node, or the NCCL sequence without a communicator."""
+    _require_cuda(students[0], "hidden_states")
+    if attn_mask is not None and not plan.cls:
+        _require_cuda(attn_mask, "attention_mask")
+    distributed, pg = resolve_group(group)
+    peer = get_peer_comm(pg) if distributed else None
+    if distributed and peer is None:
+        both = (mask_out[0], mask_out[1]) if mask_out is not None else None
+        if len({t.dtype for t in students} | {t.dtype for t in teachers}) > 1:
+            students, teachers = [s.float() for s in students], [t.float() for t in teachers]
+        return _DistillFunction.apply(plan, attn_mask, group, tuple(_prepare(teachers)), both, *students)
+    ext = node.load()
+    return ext.distill(plan.node_plan(), students, teachers, None if plan.cls else attn_mask, mask_out,
+                       peer.handle.value if peer is not None else 0, ticket, seen, cabi.active_tuning_address())
+
+
 def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor], attn_mask, plan: DistillPlan,
-                 group=None, teachers_detached: bool = False, mask_out=None):
+                 group=None, teachers_detached: bool = False, mask_out=None, ticket=None, seen=None):
     """Differentiable fused distillation loss over ``len(students)`` selected layers.
 
     Returns ``(total, aux)``: ``total`` is the 0-dim fp32 loss (gradients flow to ``students``),
     ``aux`` the non-differentiable ``[3L]`` vector of layer losses then (text, vision) losses.
-    ``mask_out``: optional pre-allocated int64 ``(lang_masks, image_masks)`` ``[B, T]`` pair, filled by the
-    step's own kernel (``attn_mask`` must then be a contiguous int64 CUDA tensor).
+    ``mask_out``: optional pre-allocated int64 ``[2, B, T]`` tensor; the step's own kernel fills ``[0]`` with
+    ``lang_masks`` and ``[1]`` with ``image_masks`` (``attn_mask`` must then be a contiguous int64 CUDA tensor).
+    ``ticket``: the token counts sent ahead of the step (``prefetch_counts``).  ``seen``: pinned float32 tensor
+    that receives the upstream gradient the backward gate saw.
     """
-    students = list(students)
-    teachers = list(teachers) if teachers_detached else [t.detach() for t in teachers]
+    if not teachers_detached:
+        teachers = [t.detach() for t in teachers]
     if len(students) != len(teachers) or len(students) != len(plan.layers):
         raise ValueError("students / teachers / plan.layers length mismatch")
-    dt = students[0].dtype
-    for t in students:
-        if t.dtype != dt:
-            break
-    else:
-        for t in teachers:
-            if t.dtype != dt:
-                break
-        else:
-            dt = None
-    if dt is not None:
-        # mixed dtypes: the reference up-casts both sides to fp32 under autocast (distillation.py:90,244)
-        students = [s.float() for s in students]
-        teachers = [t.float() for t in teachers]
-    teachers = _prepare(teachers)
+    # (layers of different dtypes: the node up-casts both sides to fp32, as the reference does under autocast,
+    # distillation.py:90,244)
     n = len(students)
     if n <= cabi.MAX_LAYERS:
-        return _DistillFunction.apply(plan, attn_mask, group, tuple(teachers), mask_out, *students)
+        return _step(plan, attn_mask, group, teachers, mask_out, students, ticket, seen)
     # more selected layers than one launch carries (MAFED_MAX_LAYERS): chunk and add the partial totals
     total, layer_losses, modal_losses = None, [], []
     for lo in range(0, n, cabi.MAX_LAYERS):
@@ -435,8 +484,8 @@ def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tens
                           loss_kind=plan.loss_kind, cls=plan.cls, n_vis=plan.n_vis,
                           grad_multiplier=plan.grad_multiplier, single_pass=plan.single_pass,
                           assumed_grad_out=plan.assumed_grad_out)
-        part, aux = _DistillFunction.apply(sub, attn_mask, group, tuple(teachers[lo:hi]), mask_out if lo == 0 else None,
-                                           *students[lo:hi])
+        part, aux = _step(sub, attn_mask, group, teachers[lo:hi], mask_out if lo == 0 else None, students[lo:hi],
+                          ticket, seen)
         total = part if total is None else total + part
         layer_losses.append(aux[: hi - lo])
         modal_losses.append(aux[hi - lo:])

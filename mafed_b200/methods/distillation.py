@@ -8,13 +8,15 @@ behind ``CLMethod["featdistill"]`` (``mafed/train.py:119-134``,
 What changed underneath: the reference loops over layers in Python and, per layer, builds two masks
 on the CPU, runs two masked token-loss passes through ~16 ATen kernels and synchronises the host for
 W&B.  Here one step is ONE kernel launch over all selected layers (masks, gradient scale, loss sums,
-gradients and the loss algebra; ``mafed_distill_step``) plus a fix-up launch in ``backward`` that returns
-at once unless the upstream gradient differs from the assumed one -- no host synchronisation; the
-per-layer values the reference logs (``task_{k}/distill_loss_{layer}``) stay on the device and are
-logged one step late.
+gradients and the loss algebra; ``mafed_distill_step``) plus, in ``backward``, a 1-CTA gate that returns at
+once unless the upstream gradient differs from the assumed one (then it starts the exact backward from the
+device) -- no host synchronisation; the per-layer values the reference logs (``task_{k}/distill_loss_{layer}``)
+stay on the device and are logged a step or two late.  The host side of a step is one call into a compiled
+autograd node (``mafed_b200.node``).
 """
 from __future__ import annotations
 
+from collections import deque
 from copy import deepcopy
 from typing import Dict, List, Optional
 
@@ -23,7 +25,7 @@ import torch
 
 from mafed_b200 import cabi
 from mafed_b200.capture import HiddenStateCapture
-from mafed_b200.distill_op import DistillPlan, distill_loss, modality_masks
+from mafed_b200.distill_op import DistillPlan, distill_loss, modality_masks, resolve_group, seen_slot
 from mafed_b200.methods.base import CLStrategy
 from mafed_b200.methods.distillation_loss_weights import DistillationWeights
 
@@ -103,6 +105,19 @@ class FeatureDistillation(CLStrategy):
         # gradient it bakes in is Lightning's 1/accumulate_grad_batches, checked on the device in backward
         self.single_pass = bool(kwargs.get("single_pass", True))
         self.assumed_grad_out = 1.0 / float(self.update_freq)
+        # The backward gate leaves the upstream gradient it really saw in a pinned word; distill() reads it (a plain
+        # host read, possibly a step old) and re-aims `assumed_grad_out`, so a trainer that scales the loss
+        # differently (a static loss scale, another accumulation factor) pays the exact backward once, not per step.
+        # An upstream gradient that keeps changing (dynamic loss scaling) switches the strategy to the two-pass form.
+        self.adapt_assumed_grad_out = bool(kwargs.get("adapt_assumed_grad_out", True))
+        self._gout_seen = self._gout_seen_np = None
+        self._gout_changes = 0
+        # Batch-sharded runs return the GLOBAL-batch loss on every rank, so each rank's hidden-state gradient is its
+        # share of dL_global/dh.  DistributedDataParallel then AVERAGES parameter gradients over the ranks, which
+        # would leave the distillation term world_size times too small next to the (per-rank mean) LM losses.
+        # None: multiply by world_size whenever the sharded path is active (right under DDP); pass 1.0 when the
+        # gradients are summed, not averaged, across ranks.
+        self.grad_multiplier = kwargs.get("grad_multiplier")
         # record only the distilled hidden states with forward hooks instead of output_hidden_states=True
         self.selective_capture = bool(kwargs.get("selective_capture", False))
         # walk one memory-loader iterator instead of spawning a fresh one per replay step
@@ -112,7 +127,8 @@ class FeatureDistillation(CLStrategy):
         self._plan_cache = None
         self.last_layer_losses: Optional[torch.Tensor] = None   # device [3L]: layer, then (text, vision)
         self.last_layers: List[int] = []
-        self._pending_log = None
+        self._pending_logs = deque()
+        self._ticket = None                                  # (attention_mask, its version, ticket) of prefetch_counts
 
     # ------------------------------------------------------------------ trainer hooks
     def update(self, dataset, model, dataloader, mask=None, **kwargs):
@@ -147,6 +163,9 @@ class FeatureDistillation(CLStrategy):
         n_ex = batch["input_ids"].size(0)
         do_replay = self.replay_coeff > 0 and self.task_id > 0
         loss = None
+        if self.distillation_coeff != 0 and not self._cls_distillation:
+            # batch-sharded: this rank's token counts leave for the peers now, behind the student forward
+            self.prefetch_counts(batch)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             if self.selective_capture and self.distillation_coeff != 0:
                 # keep only the distilled entries of the hidden-state tuple alive
@@ -183,11 +202,39 @@ class FeatureDistillation(CLStrategy):
             self._mem_iter = iter(self.mem_dataloader)
             return next(self._mem_iter)
 
+    def prefetch_counts(self, batch, force: bool = False):
+        """Send this rank's token counts to the peers ahead of the step (batch-sharded runs).  The counts depend
+        only on ``attention_mask``, which is known as soon as the memory batch is drawn -- before the student
+        forward (``distillation.py:85-91``) -- so the step's kernel later finds the global counts in its own
+        mailbox instead of exchanging them at its start.  ``replay`` calls this itself; a trainer that draws batches
+        ahead may call it up to two steps early.  No-op on a single rank unless ``force``."""
+        attn = batch.get("attention_mask") if hasattr(batch, "get") else None
+        if attn is None or not attn.is_cuda or attn.dtype != torch.int64 or not attn.is_contiguous():
+            return None
+        peer = self._peer()
+        if peer is None and not force:
+            return None
+        from mafed_b200 import node
+        ticket = node.load().prefetch_counts(attn, self.num_vision_tokens, peer.handle.value if peer is not None else 0,
+                                             cabi.active_tuning_address())
+        self._ticket = (attn, attn._version, ticket)
+        return ticket
+
+    def _peer(self):
+        """The peer-memory communicator of a batch-sharded run (None: single rank, or the NCCL sequence)."""
+        distributed, pg = resolve_group(self.process_group)
+        if not distributed:
+            return None
+        from mafed_b200.comm import get_peer_comm
+        return get_peer_comm(pg)
+
     def distill(self, output, batch):
         """Sum over the selected layers of ``layer_coeff * distillation_coeff * layer_loss``
         (``distillation.py:105-122``) -- as one fused launch instead of a Python loop."""
         past_hidden_states = self._get_past_hidden_states(batch)
         layers = self.loss_weights.get_distillation_layers()
+        if self.adapt_assumed_grad_out and self._gout_seen_np is not None:
+            self._adapt_assumed()
         plan = self._step_plan(layers)
         hidden = output.hidden_states
         total, aux = self._launch(plan, batch, [hidden[l] for l in layers], [past_hidden_states[l] for l in layers],
@@ -203,7 +250,7 @@ class FeatureDistillation(CLStrategy):
         coeff = getattr(lw, "lang_coeff", None)
         key = (tuple(layers), self.distillation_coeff, self._cls_distillation, self._loss_kind, self.num_vision_tokens,
                self.single_pass, self.assumed_grad_out, lw._modality_weighing_strategy, id(coeff),
-               getattr(coeff, "_version", None), id(lw.layer_coeffs))
+               getattr(coeff, "_version", None), id(lw.layer_coeffs), self.grad_multiplier, self.process_group)
         if self._plan_cache is None or self._plan_cache[0] != key:
             coeffs, modality_kind, lang_weights = self._tables(layers)
             plan = self._plan(layers, coeffs, self.distillation_coeff, modality_kind, lang_weights)
@@ -234,25 +281,54 @@ class FeatureDistillation(CLStrategy):
             # quirk kept from the reference: MSELoss takes two arguments, the CLS branch passes three
             raise TypeError("cls_distillation requires distillation_loss='cosine' "
                             "(MSELoss.forward() takes 3 positional arguments but 4 were given)")
+        mul = self.grad_multiplier
+        if mul is None:
+            distributed, pg = resolve_group(self.process_group)
+            mul = float(torch.distributed.get_world_size(pg)) if distributed else 1.0
         return DistillPlan(layers=list(layers), layer_coeffs=list(coeffs), distill_coeff=float(distill_coeff),
                            modality_kind=modality_kind, lang_weights=lang_weights, loss_kind=self._loss_kind,
                            cls=bool(self._cls_distillation), n_vis=self.num_vision_tokens,
-                           single_pass=self.single_pass, assumed_grad_out=self.assumed_grad_out)
+                           single_pass=self.single_pass, assumed_grad_out=self.assumed_grad_out,
+                           grad_multiplier=float(mul))
+
+    def _adapt_assumed(self):
+        """Re-aim the one-pass step at the upstream gradient the gate last saw (see ``__init__``)."""
+        seen = float(self._gout_seen_np[0])
+        if seen == 0.0 or seen != seen or seen in (float("inf"), float("-inf")):
+            return
+        mul = self._plan_cache[1].grad_multiplier if self._plan_cache is not None else 1.0
+        want = seen / mul
+        if abs(want - self.assumed_grad_out) <= 1e-7 * abs(want):
+            return
+        self.assumed_grad_out = want
+        self._gout_changes += 1
+        if self._gout_changes > 8 and self.single_pass:
+            # the upstream gradient is not a constant of this run: stop guessing
+            self.single_pass = False
 
     def _launch(self, plan: DistillPlan, batch, students, teachers, teachers_detached=False):
-        attn, mask_out = None, None
+        attn, mask_out, ticket = None, None, None
         if not plan.cls:
             attn = batch["attention_mask"]
             if self.populate_batch_masks:
                 if attn.is_cuda and attn.dtype == torch.int64 and attn.is_contiguous():
                     # the masks the reference leaves in `batch` are written by the step's own kernel
-                    both = torch.empty((2, attn.shape[0], self.num_vision_tokens + attn.shape[1]),
-                                       dtype=torch.int64, device=attn.device)
-                    batch["lang_masks"], batch["image_masks"] = mask_out = (both[0], both[1])
+                    mask_out = torch.empty((2, attn.shape[0], self.num_vision_tokens + attn.shape[1]),
+                                           dtype=torch.int64, device=attn.device)
+                    batch["lang_masks"], batch["image_masks"] = mask_out[0], mask_out[1]
                 else:
                     batch["lang_masks"], batch["image_masks"] = modality_masks(attn, self.num_vision_tokens)
+            tk = self._ticket
+            if tk is not None:
+                self._ticket = None
+                if tk[0] is attn and tk[1] == attn._version:
+                    ticket = tk[2]
+        if plan.single_pass and self._gout_seen is None:
+            self._gout_seen = seen_slot()
+            self._gout_seen_np = self._gout_seen.numpy()
         return distill_loss(students, teachers, attn, plan, group=self.process_group,
-                            teachers_detached=teachers_detached, mask_out=mask_out)
+                            teachers_detached=teachers_detached, mask_out=mask_out, ticket=ticket,
+                            seen=self._gout_seen if plan.single_pass else None)
 
     def _get_past_hidden_states(self, batch):
         with torch.no_grad():
@@ -291,40 +367,55 @@ class FeatureDistillation(CLStrategy):
 
     # ------------------------------------------------------------------ logging without host syncs
     def _record(self, aux: torch.Tensor, layers: List[int]):
-        """Keep the per-layer losses on the device; hand last step's values to W&B once they have
-        landed in pinned memory (the reference calls ``.item()`` per layer, ``distillation.py:165``)."""
-        self.flush_logs(wait=False)
+        """Keep the per-layer losses on the device; hand earlier steps' values to W&B once they have landed in
+        pinned memory (the reference calls ``.item()`` per layer, ``distillation.py:165``).  Every step's values
+        are logged, in order: a step whose copy has not completed yet stays queued."""
         self.last_layer_losses = aux
         self.last_layers = list(layers)
+        self.check_exchange(sync=False)
         if _wandb is None or getattr(_wandb, "run", None) is None:
             return
+        self.flush_logs(wait=False)
         host = torch.empty(len(layers), dtype=torch.float32, pin_memory=True)
         host.copy_(aux[: len(layers)], non_blocking=True)
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(aux.device))
-        self._pending_log = (host, done, list(layers), self.task_id)
+        self._pending_logs.append((host, done, list(layers), self.task_id))
+        while len(self._pending_logs) > 64:     # the host is far ahead of the device: wait for the oldest step
+            self._flush_one(wait=True)
+
+    def _flush_one(self, wait: bool) -> bool:
+        host, done, layers, task_id = self._pending_logs[0]
+        if not wait and not done.query():
+            return False
+        done.synchronize()
+        self._pending_logs.popleft()
+        if _wandb is not None and getattr(_wandb, "run", None) is not None:
+            # one `wandb.log` per layer, like the reference (distillation.py:165): W&B's step axis advances L times
+            # per replay step either way
+            for l, v in zip(layers, host.tolist()):
+                _wandb.log({f"task_{task_id}/distill_loss_{l}": float(v)})
+        return True
 
     def flush_logs(self, wait: bool = True):
-        """Send the pending per-layer values to W&B (``task_{id}/distill_loss_{layer}``)."""
-        if self._pending_log is None:
-            return
-        host, done, layers, task_id = self._pending_log
-        if not wait and not done.query():
-            return
-        done.synchronize()
-        self._pending_log = None
-        if _wandb is not None and getattr(_wandb, "run", None) is not None:
-            _wandb.log({f"task_{task_id}/distill_loss_{l}": float(v) for l, v in zip(layers, host.tolist())})
+        """Send the queued per-layer values to W&B (``task_{id}/distill_loss_{layer}``), oldest first."""
+        while self._pending_logs and self._flush_one(wait):
+            pass
 
-    def check_exchange(self):
-        """Batch-sharded runs: raise if a peer missed an in-kernel exchange (that step's results are NaN).
-        Synchronises the device; called where the host reads the losses anyway."""
+    def check_exchange(self, sync: bool = True):
+        """Batch-sharded runs: raise if a peer missed an in-kernel exchange (that step's loss and gradients are NaN;
+        every rank must run the same number of distillation steps).  The status word lives in mapped pinned host
+        memory, so reading it costs nothing: ``distill`` does it every step (``sync=False``: it sees every step
+        that has FINISHED, i.e. a missed exchange raises one step late at the latest, before the poisoned
+        gradients can survive an optimizer step unnoticed); ``sync=True`` waits for the queued steps first."""
         from mafed_b200.comm import peek_peer_comm
         group = self.process_group
         if group is False:
             return
         peer = peek_peer_comm(None if group is None or group is True else group)
         if peer is not None:
+            if sync:
+                torch.cuda.synchronize()
             peer.check()
 
     def layer_loss_dict(self) -> Dict[str, float]:
@@ -358,12 +449,16 @@ class FeatureDistillation(CLStrategy):
         self.rng.bit_generator.state = state["rng_state"]
         coeff = state.get("lang_coeff")
         if coeff is not None:
+            if torch.is_tensor(coeff) and torch.cuda.is_available():
+                coeff = coeff.cuda()     # `update_weights` averages it with importances computed on the device
             self.loss_weights.lang_coeff = coeff
             self.loss_weights._lang_coeff_host = None
         self._plan_cache = None
         if datasets is not None:
             from torch.utils.data import Subset
             self.datasets = [Subset(ds, idx) for ds, idx in zip(datasets, state["memory_indices"])]
+            if self.datasets:
+                self._rebuild_loader()
 
     # ------------------------------------------------------------------ between tasks
     def _update_model(self, model):
@@ -375,16 +470,21 @@ class FeatureDistillation(CLStrategy):
         """Add ``memory_per_task`` random samples of the finished task to the episodic memory and
         rebuild its loader (``distillation.py:182-209``).  Data loading itself is the reference's
         (``mafed.data``); it is imported lazily because it is outside this package's scope."""
-        from torch.utils.data import ConcatDataset, DataLoader, RandomSampler, Subset
-        from torch.utils.data.distributed import DistributedSampler
-        import torch.distributed as dist
-
-        if self.task_id > 0:
+        from torch.utils.data import Subset
+        if hasattr(self, "mem_dataloader"):
             del self.mem_dataloader
         picked = self.rng.choice(np.arange(len(dataset)), self.memory_per_task, replace=False)
         assert len(set(picked)) == self.memory_per_task
         self.seed = 1
         self.datasets.append(Subset(dataset, picked))
+        self._rebuild_loader()
+
+    def _rebuild_loader(self):
+        """(Re)create the memory loader over ``self.datasets`` (``distillation.py:192-209``)."""
+        from torch.utils.data import ConcatDataset, DataLoader, RandomSampler
+        from torch.utils.data.distributed import DistributedSampler
+        import torch.distributed as dist
+
         memory = ConcatDataset(self.datasets)
         distributed = dist.is_available() and dist.is_initialized()
         sampler = DistributedSampler(memory) if distributed else RandomSampler(memory)

@@ -21,7 +21,9 @@ int main(void) {
   shape.dtype = MAFED_BF16;
   w.modality_kind = MAFED_MODW_EQUAL; w.distill_coeff = 1.0f; w.layer_coeff[0] = 1.0f;
   if (mafed_distill_step(&shape, NULL, NULL, NULL, NULL, &w, 1.0f, NULL, NULL, NULL, NULL, NULL, NULL, NULL,
-                         NULL) != MAFED_E_ARG) ++failures;
+                         NULL, NULL) != MAFED_E_ARG) ++failures;
+  if (mafed_distill_bwd(&shape, NULL, NULL, NULL, NULL, NULL, NULL, 1.0f, NULL, NULL, NULL) != MAFED_E_ARG) ++failures;
+  if (mafed_distill_prefetch_counts(&shape, NULL, NULL, NULL, NULL) != MAFED_E_ARG) ++failures;
   if (strstr(mafed_distill_error_string(MAFED_E_ALIGN), "aligned") == NULL) ++failures;
   printf("%s\n", failures ? "FAIL" : "OK");
   return failures;

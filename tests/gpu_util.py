@@ -36,8 +36,7 @@ def make_method(meta, **extra):
 def run_product(meta, students, teachers, mask, grad_out=1.0, variant=cabi.VARIANT_DEFAULT, dev="cuda",
                 single_pass=True, accumulate=1):
     """distill() + backward() on the GPU through the mirrored strategy API."""
-    cabi.load().mafed_distill_set_variant(variant)
-    try:
+    with cabi.tuning(variant=variant):
         fd = make_method(meta, single_pass=single_pass)
         fd.assumed_grad_out = 1.0 / accumulate
         st = [s.to(dev).detach().clone().requires_grad_(True) for s in students]
@@ -49,8 +48,6 @@ def run_product(meta, students, teachers, mask, grad_out=1.0, variant=cabi.VARIA
         torch.cuda.synchronize()
         return dict(loss=loss.detach().float().cpu(), grads=[None if s.grad is None else s.grad.cpu() for s in st],
                     layer_dict=fd.layer_loss_dict(), batch=batch, fd=fd, students=st)
-    finally:
-        cabi.load().mafed_distill_set_variant(cabi.VARIANT_DEFAULT)
 
 
 def rel_err(a, b):

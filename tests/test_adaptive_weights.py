@@ -90,9 +90,7 @@ def test_compute_adaptive_weights_on_gpu_matches_reference():
 def test_token_norm_sums_kernel(variant, dtype, dim):
     from mafed_b200 import cabi
     from mafed_b200.distill_op import token_norm_sums
-    lib = cabi.load()
-    lib.mafed_distill_set_variant(variant)
-    try:
+    with cabi.tuning(variant=variant):
         g = torch.Generator(device="cuda").manual_seed(5)
         B, txt, n_layers = 5, 9, 4
         grads = [torch.randn(B, 256 + txt, dim, generator=g, device="cuda").to(dtype) * (0.1 + l) for l in range(n_layers)]
@@ -107,5 +105,3 @@ def test_token_norm_sums_kernel(variant, dtype, dim):
             assert float(sums[2 * l]) == pytest.approx(float((norm * lang_mask).sum()), rel=tol)
             assert float(sums[2 * l + 1]) == pytest.approx(float((norm * image_mask).sum()), rel=tol)
         assert float(sums[-2]) == float(am.sum()) and float(sums[-1]) == B * 256
-    finally:
-        lib.mafed_distill_set_variant(0)

@@ -36,8 +36,7 @@ def _inputs(cfg, dtype=torch.bfloat16, seed=1234, ragged=True):
 
 
 def _run(meta, st, te, am, grad_out=1.0, variant=cabi.VARIANT_DEFAULT):
-    cabi.load().mafed_distill_set_variant(variant)
-    try:
+    with cabi.tuning(variant=variant):
         fd = make_method(meta)
         leaves = [s.detach().requires_grad_(True) for s in st]
         fd.past_model = lambda **kw: Out(tuple(te))
@@ -45,8 +44,6 @@ def _run(meta, st, te, am, grad_out=1.0, variant=cabi.VARIANT_DEFAULT):
         (loss * grad_out).backward()
         torch.cuda.synchronize()
         return loss.detach(), [l.grad for l in leaves], fd
-    finally:
-        cabi.load().mafed_distill_set_variant(cabi.VARIANT_DEFAULT)
 
 
 def _torch_reference(meta, st, te, am, nh, gamma=0.5):

@@ -16,7 +16,8 @@ def test_raw_ctypes_stub_two_pass_and_backward():
     lib.mafed_distill_error_string.restype = ctypes.c_char_p
 
     class Shape(ctypes.Structure):
-        _fields_ = [(n, ctypes.c_int32) for n in ("n_layers", "B", "T", "n_vis", "D", "dtype", "loss_kind", "cls")]
+        _fields_ = [(n, ctypes.c_int32) for n in ("n_layers", "B", "T", "n_vis", "D", "dtype", "loss_kind", "cls")] + \
+                   [("tuning", ctypes.c_void_p)]
 
     class Weights(ctypes.Structure):
         _fields_ = [("modality_kind", ctypes.c_int32), ("distill_coeff", ctypes.c_float),
@@ -35,7 +36,7 @@ def test_raw_ctypes_stub_two_pass_and_backward():
     mask = am.cuda()
     L = 3
     B, T, D = students[0].shape
-    sh = Shape(L, B, T, 256, D, 0, 0, 0)
+    sh = Shape(L, B, T, 256, D, 0, 0, 0, None)
     w = Weights(1, 1.0)
     w.layer_coeff[:L] = [float(c) for c in coeffs]
     w.lang_weight[:L] = [0.5] * L
@@ -47,13 +48,15 @@ def test_raw_ctypes_stub_two_pass_and_backward():
     rc = lib.mafed_distill_fwd(ctypes.byref(sh), ptrs(students), ptrs(teachers), vp(mask.data_ptr()),
                                vp(ws.data_ptr()), vp(stream))
     assert rc == 0, lib.mafed_distill_error_string(rc)
-    rc = lib.mafed_distill_epilogue(ctypes.byref(sh), ctypes.byref(w), vp(mask.data_ptr()), vp(ws.data_ptr()), None,
-                                    vp(out.data_ptr()), vp(scale.data_ptr()), vp(stream))
+    REDUCE, COUNTS, LOSSES, SCALE = 1, 2, 4, 8
+    rc = lib.mafed_distill_scalar_stage(ctypes.byref(sh), ctypes.byref(w), REDUCE | COUNTS | LOSSES | SCALE,
+                                        vp(mask.data_ptr()), vp(ws.data_ptr()), None, vp(out.data_ptr()),
+                                        vp(scale.data_ptr()), None, 0, vp(stream))
     assert rc == 0
     grads = [torch.empty_like(s) for s in students]
     gout = torch.tensor(0.25, device="cuda")
     rc = lib.mafed_distill_bwd(ctypes.byref(sh), ptrs(students), ptrs(teachers), ptrs(grads), vp(mask.data_ptr()),
-                               vp(scale.data_ptr()), vp(gout.data_ptr()), None, vp(stream))
+                               vp(scale.data_ptr()), vp(gout.data_ptr()), ctypes.c_float(1.0), None, None, vp(stream))
     assert rc == 0
     torch.cuda.synchronize()
     assert float(out[0]) == pytest.approx(float(ref["loss"]), rel=1e-5)

@@ -15,10 +15,6 @@ from oracle import distill_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _tune(key, value):
-    cabi.check(cabi.load().mafed_distill_set_tuning(key, value), "set_tuning")
-
-
 def _inputs(B, txt, D, L, dtype, seed, ragged=True):
     st, te, am = O.make_inputs(L + 1, B, txt, D, n_vis=256, dtype=dtype, seed=seed)
     if not ragged:
@@ -49,15 +45,12 @@ def test_one_launch_step_equals_separate_launches(dtype, loss, modality):
     mask = am.cuda()
     results = []
     for no_tail in (0, 1):
-        _tune(cabi.TUNE_NO_TAIL, no_tail)
-        try:
+        with cabi.tuning(TUNE_NO_TAIL=no_tail):
             g = [torch.full_like(x, float("nan")) for x in s]
             both = torch.full((2, 6, 256 + 9), -7, dtype=torch.int64, device="cuda")
             out, scale, ln = distill_fused(s, t, g, mask, plan, group=False, mask_out=(both[0], both[1]))
             torch.cuda.synchronize()
             results.append((out.clone(), [x.clone() for x in g], both.clone()))
-        finally:
-            _tune(cabi.TUNE_NO_TAIL, 0)
     (o1, g1, m1), (o2, g2, m2) = results
     assert torch.equal(o1, o2)                                   # same fixed-order reduction, wherever it runs
     assert all(torch.equal(a, b) for a, b in zip(g1, g2))
@@ -82,15 +75,12 @@ def test_forward_step_equals_forward_plus_epilogue(dtype):
     gout = torch.full((), 0.5, device="cuda")
     results = []
     for no_tail in (0, 1):
-        _tune(cabi.TUNE_NO_TAIL, no_tail)
-        try:
+        with cabi.tuning(TUNE_NO_TAIL=no_tail):
             out, scale, ln = distill_forward(s, t, mask, plan, group=False)
             g = [torch.empty_like(x) for x in s]
             distill_backward(ln, g, scale, gout)
             torch.cuda.synchronize()
             results.append((out.clone(), g))
-        finally:
-            _tune(cabi.TUNE_NO_TAIL, 0)
     assert torch.equal(results[0][0], results[1][0])
     assert all(torch.equal(a, b) for a, b in zip(results[0][1], results[1][1]))
     ref = O.forward_backward(st, te, am, cfg, grad_out=0.5)
@@ -111,15 +101,12 @@ def test_large_mask_step_keeps_the_tail():
     mask = am.cuda()
     results = []
     for no_tail in (0, 1):
-        _tune(cabi.TUNE_NO_TAIL, no_tail)
-        try:
+        with cabi.tuning(TUNE_NO_TAIL=no_tail):
             g = [torch.empty_like(x) for x in s]
             both = torch.empty((2, B, 256 + txt), dtype=torch.int64, device="cuda")
             out, scale, ln = distill_fused(s, t, g, mask, plan, group=False, mask_out=(both[0], both[1]))
             torch.cuda.synchronize()
             results.append((out.clone(), g, both))
-        finally:
-            _tune(cabi.TUNE_NO_TAIL, 0)
     assert torch.equal(results[0][0], results[1][0])
     assert all(torch.equal(a, b) for a, b in zip(results[0][1], results[1][1]))
     assert torch.equal(results[0][2], results[1][2])
@@ -177,7 +164,7 @@ def test_step_through_the_c_abi_with_every_output():
     rc = lib.mafed_distill_step(ctypes.byref(shape), cabi.ptr_array([x.data_ptr() for x in s]),
                                 cabi.ptr_array([x.data_ptr() for x in t]), cabi.ptr_array([x.data_ptr() for x in g]),
                                 mask.data_ptr(), ctypes.byref(plan.weights()), 1.0, ws.data_ptr(), out.data_ptr(),
-                                scale.data_ptr(), sums.data_ptr(), both[0].data_ptr(), both[1].data_ptr(), None,
+                                scale.data_ptr(), sums.data_ptr(), both[0].data_ptr(), both[1].data_ptr(), None, None,
                                 torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     torch.cuda.synchronize()
@@ -193,7 +180,7 @@ def test_step_through_the_c_abi_with_every_output():
     # argument errors: masks come as a pair; sharded steps need the sums vector
     assert lib.mafed_distill_step(ctypes.byref(shape), None, None, None, None, ctypes.byref(plan.weights()), 1.0,
                                   ws.data_ptr(), out.data_ptr(), scale.data_ptr(), None, both[0].data_ptr(), None,
-                                  None, None) == -1
+                                  None, None, None) == -1
 
 
 def test_autograd_op_fills_the_batch_masks():
@@ -203,7 +190,7 @@ def test_autograd_op_fills_the_batch_masks():
     t = [te[l].cuda() for l in plan.layers]
     mask = am.cuda()
     both = torch.zeros((2, 3, 261), dtype=torch.int64, device="cuda")
-    total, aux = distill_loss(s, t, mask, plan, group=False, mask_out=(both[0], both[1]))
+    total, aux = distill_loss(s, t, mask, plan, group=False, mask_out=both)
     total.backward()
     lang, image = modality_masks(mask, 256)
     assert torch.equal(both[0], lang) and torch.equal(both[1], image)
@@ -238,7 +225,7 @@ def test_missing_peer_poisons_the_step_instead_of_hanging():
         rc = lib.mafed_distill_step(ctypes.byref(shape), cabi.ptr_array([x.data_ptr() for x in s]),
                                     cabi.ptr_array([x.data_ptr() for x in t]), cabi.ptr_array([x.data_ptr() for x in g]),
                                     mask.data_ptr(), ctypes.byref(plan.weights()), 1.0, ws.data_ptr(), out.data_ptr(),
-                                    scale.data_ptr(), sums.data_ptr(), None, None, handle,
+                                    scale.data_ptr(), sums.data_ptr(), None, None, handle, None,
                                     torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         torch.cuda.synchronize()

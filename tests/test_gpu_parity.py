@@ -240,7 +240,7 @@ def test_sharded_partial_sums_equal_full_batch():
         ws = torch.empty(lib.mafed_distill_ws_bytes(L), dtype=torch.uint8, device="cuda")
         sums = torch.empty(2 * L + 2, dtype=torch.float64, device="cuda")
         cabi.check(lib.mafed_distill_fwd(ctypes.byref(ln.shape), ln.s_ptrs, ln.t_ptrs, ln.mask_ptr, ws.data_ptr(), stream), "fwd")
-        cabi.check(lib.mafed_distill_reduce(ctypes.byref(ln.shape), ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream), "reduce")
+        cabi.check(cabi.reduce_stage(lib, ctypes.byref(ln.shape), ln.mask_ptr, ws.data_ptr(), sums.data_ptr(), stream), "reduce")
         torch.cuda.synchronize()
         return sums, ln
 
@@ -253,8 +253,8 @@ def test_sharded_partial_sums_equal_full_batch():
     scale = torch.empty(2 * L, dtype=torch.float32, device="cuda")
     w = plan.weights()
     merged = (a + b).contiguous()
-    cabi.check(lib.mafed_distill_finalize(ctypes.byref(ln_full.shape), ctypes.byref(w), merged.data_ptr(),
-                                          out.data_ptr(), scale.data_ptr(), stream), "finalize")
+    cabi.check(cabi.finalize_stage(lib, ctypes.byref(ln_full.shape), ctypes.byref(w), merged.data_ptr(),
+                                   out.data_ptr(), scale.data_ptr(), stream), "finalize")
     torch.cuda.synchronize()
     cfg = O.OracleConfig(modality_strategy="equal", layer_strategy="discounted", num_hidden_layers=3,
                          distillation_layer=None, num_vision_tokens=256)
@@ -353,13 +353,19 @@ def test_wandb_values_are_logged_late_without_host_sync(monkeypatch):
     torch.cuda.synchronize()
     assert logged == []                                   # nothing forced the host to wait during the step
     fd.distill(Out(tuple(leaves)), {"attention_mask": am.cuda()})   # the next step hands over the previous values
-    assert len(logged) == 1 and set(logged[0]) == {f"task_2/distill_loss_{l}" for l in range(3)}
+    # one wandb.log call per layer, in layer order, exactly like the reference's loop (distillation.py:165)
+    assert [list(d) for d in logged] == [[f"task_2/distill_loss_{l}"] for l in range(3)]
     for l in range(3):
-        assert logged[0][f"task_2/distill_loss_{l}"] == pytest.approx(float(ref["layer_losses"][l]), rel=1e-5)
+        assert logged[l][f"task_2/distill_loss_{l}"] == pytest.approx(float(ref["layer_losses"][l]), rel=1e-5)
     fd.flush_logs()
-    assert len(logged) == 2 and logged[1] == pytest.approx(logged[0])
+    assert len(logged) == 6 and [list(d.values()) for d in logged[3:]] == pytest.approx([list(d.values()) for d in logged[:3]])
     fd.flush_logs()
-    assert len(logged) == 2
+    assert len(logged) == 6
+    # every step is logged even when the host runs ahead of the device (values used to be dropped)
+    for _ in range(5):
+        fd.distill(Out(tuple(leaves)), {"attention_mask": am.cuda()})
+    fd.flush_logs()
+    assert len(logged) == 6 + 5 * 3
 
 
 def test_inplace_modification_between_forward_and_backward_is_detected():

@@ -189,8 +189,24 @@ def test_strategy_state_roundtrip():
     state = fd.state_dict()
     nxt = fd.rng.choice(np.arange(100), 5, replace=False)
     other = FeatureDistillation(8, Opts(), "vlpythia", **kw)
+    other.num_workers = 0
+    other.data_hooks = (_collate, lambda loader: loader)
     other.load_state_dict(state, datasets=[_ToyDataset(50)])
     assert (other.task_id, other.step) == (1, 17)
     assert sorted(other.datasets[0].indices) == sorted(fd.datasets[0].indices)
     assert other.loss_weights.kernel_tables()[2] == pytest.approx([0.3, 0.7])
     assert (other.rng.choice(np.arange(100), 5, replace=False) == nxt).all()   # sampling continues identically
+    # a restored strategy can RUN: the memory loader exists again, the next task's update() works
+    batch = other._next_memory_batch()
+    assert batch["input_ids"].shape[0] == min(Opts.batch_size, other.memory_per_task)
+    assert other.mem_sampler is not None
+    other.loss_weights.update_weights = lambda model, dataloader, task_id: None   # (needs a model; not this test)
+    other.update(dataset=_ToyDataset(60), model=torch.nn.Linear(2, 2), dataloader=None)
+    assert other.task_id == 2 and len(other.datasets) == 2 and other.past_model is not None
+    assert len(other.mem_dataloader.dataset) == 2 * other.memory_per_task
+    # a fresh strategy restored WITHOUT datasets still updates (no stale `del self.mem_dataloader`)
+    bare = FeatureDistillation(8, Opts(), "vlpythia", **kw)
+    bare.num_workers, bare.data_hooks = 0, (_collate, lambda loader: loader)
+    bare.load_state_dict(state)
+    bare._update_memory(_ToyDataset(50))
+    assert len(bare.datasets) == 1
