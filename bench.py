@@ -4,10 +4,22 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C2|C3|C1] [--impl ours|reference]
 
 Metric (BASELINE.json): distill fwd+bwd tokens*layers/sec, and the fraction of HBM peak.
-A "step" is one pass of the hot path (forward over all selected layers, epilogue, backward) over one
-synthetic batch of hidden states.  Default workload: the VLPythia-1B shape the metric is quoted on
-(C4: 16 layers -> 15 distilled, D=2048, T=256+32, bf16) at 64 samples per GPU, i.e. weak scaling to
-C4's global batch 512 on 8 GPUs.  Prints ONE JSON line on rank 0.
+A "step" is one pass of the hot path (forward over all selected layers, loss algebra, backward) over one
+synthetic batch of hidden states, through the call a user makes: ``FeatureDistillation.distill`` then
+``loss.backward()``.  Default workload: the VLPythia-1B shape the metric is quoted on (C4: 16 layers -> 15
+distilled, D=2048, T=256+32, bf16) at 64 samples per GPU, i.e. weak scaling to C4's global batch 512 on 8 GPUs.
+Prints ONE JSON line on rank 0.  Besides the contract's keys the line carries:
+
+  roofline          the fused kernel against the measured HBM peak (CUDA events around every launch)
+  two_pass          north_star's two-kernel form (5*D*e bytes per token*layer)
+  other_workloads   C2 / C3 / C1 and cosine / fp32-input variants through the same API (N=1)
+  c5                BASELINE configs[4]: per-GPU batch 8..128 x text 32 / 256 x all-ones / ragged masks, through
+                    the API and at kernel level, at this N
+  sharded_parity    (N>1) one small ragged step sharded over the ranks against the same step on the concatenated
+                    batch on one GPU and against the CPU oracle; the run FAILS if it is out of tolerance
+  e2e               the same metric with HOST buffers through the C ABI's host step (copies inside the timed region)
+  cpu_baseline      the UNMODIFIED reference (oracle/_ref) on the host cores, full per-GPU shard
+``--impl reference`` times that unmodified reference alone (rank 0 only).
 """
 from __future__ import annotations
 
@@ -163,40 +175,67 @@ class Out:
         self.hidden_states = hs
 
 
-def make_method(n_sel):
+def make_method(n_sel, loss=None):
     from mafed_b200.methods import CLMethod
     return CLMethod["featdistill"](
         memory_size=8, opts=Opts(), model_type="vlpythia",
         distillation_modality_weighing_strategy=RECIPE["modality"],
         distillation_layer_weighing_strategy=RECIPE["layer_strategy"], distillation_coeff=1.0,
-        distillation_layer=None, distillation_loss=RECIPE["loss"], gamma=RECIPE["gamma"], num_hidden_layers=n_sel)
+        distillation_layer=None, distillation_loss=loss or RECIPE["loss"], gamma=RECIPE["gamma"],
+        num_hidden_layers=n_sel)
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_baseline(wl, sample_B=None, iters=3, warmup=1):
-    """The reference's op chain (oracle port, torch CPU ops + autograd) on the host cores."""
+# ----------------------------------------------------------------------------- CPU baseline (the unmodified reference)
+def cpu_reference_steps(wl, steps, warmup, budget_s=150.0):
+    """``FeatureDistillation.distill`` + ``backward()`` of the UNMODIFIED reference (oracle/_ref: byte-identical
+    copies of mafed/methods/*.py, imported with stubbed third-party modules) on CPU tensors of the full per-GPU
+    shard, under ``torch.autocast("cpu", bfloat16)`` for the bf16 workloads (what ``replay`` does on the GPU,
+    distillation.py:90), with every host thread torch can use.  If the reference files are not there the oracle
+    restatement is timed instead and says so (kind "port")."""
     from oracle import distill_oracle as O
+    from oracle import ref_harness as R
     _, n_tuple, n_sel, B, txt, D, dt = WORKLOADS[wl]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    if sample_B is None:
-        sample_B = max(1, min(B, int(16 * 2048 / D)))
-    st, te, am = O.make_inputs(n_sel, sample_B, txt, D, n_vis=N_VIS, dtype=torch_dtype(dt), seed=1234,
-                               teacher="close", mask="full")
-    cfg = O.OracleConfig(modality_strategy=RECIPE["modality"], layer_strategy=RECIPE["layer_strategy"],
-                         gamma=RECIPE["gamma"], num_hidden_layers=n_sel, distillation_layer=None, loss=RECIPE["loss"],
-                         num_vision_tokens=N_VIS)
-    times = []
-    for i in range(warmup + iters):
+    st, te, am = O.make_inputs(n_sel, B, txt, D, n_vis=N_VIS, dtype=torch_dtype(dt), seed=1234, teacher="close",
+                               mask="full")
+    kind = "reference" if R.available() else "port"
+    if kind == "reference":
+        fd = R.make_reference_method(modality=RECIPE["modality"], layer_strategy=RECIPE["layer_strategy"],
+                                     loss=RECIPE["loss"], gamma=RECIPE["gamma"], num_hidden_layers=n_sel, n_vis=N_VIS)
+
+        def step():
+            return R.reference_forward_backward(fd, st, te, am, autocast_bf16=(dt != "fp32"))["loss"]
+    else:
+        cfg = O.OracleConfig(modality_strategy=RECIPE["modality"], layer_strategy=RECIPE["layer_strategy"],
+                             gamma=RECIPE["gamma"], num_hidden_layers=n_sel, distillation_layer=None,
+                             loss=RECIPE["loss"], num_vision_tokens=N_VIS)
+
+        def step():
+            return O.forward_backward(st, te, am, cfg)["loss"]
+    times, loss = [], None
+    t_start = time.perf_counter()
+    done_warm = 0
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.forward_backward(st, te, am, cfg)
+        loss = step()
+        dt_s = time.perf_counter() - t0
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    units = sample_B * (N_VIS + txt) * n_sel
-    return {"value": units / min(times), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{wl} shape, B={sample_B} of {B} samples, {n_sel} layers, {dt}, torch CPU ops + autograd "
-                      f"(oracle port of distillation.py:105-166), best of {iters}",
-            "ms_per_sample_step": 1e3 * min(times)}
+            times.append(dt_s)
+        else:
+            done_warm += 1
+        if time.perf_counter() - t_start + dt_s > budget_s and times:
+            break    # bounded: never let the baseline leg run for more than a few minutes
+    units = B * (N_VIS + txt) * n_sel
+    mean_s = sum(times) / len(times)
+    what = ("unmodified reference FeatureDistillation.distill + backward (oracle/_ref, mafed/methods/distillation.py:105-166)"
+            if kind == "reference" else "oracle restatement of distillation.py:105-166 (reference files absent)")
+    return {"value": units / mean_s, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{wl} per-GPU shard at full size: B={B} of {B} samples, {n_sel} layers, T={N_VIS + txt}, D={D}, {dt}"
+                      f"{' under torch.autocast(cpu, bfloat16)' if dt != 'fp32' else ''}; {what}; torch CPU ops + autograd on "
+                      f"{cores} threads; mean of {len(times)} steps after {done_warm} warm-up",
+            "ms_per_step": 1e3 * mean_s, "best_ms": 1e3 * min(times), "steps_run": len(times), "warmup_run": done_warm,
+            "loss": float(loss)}
 
 
 def eager_gpu_baseline(wl, st, te, am, iters=5, warmup=2):
@@ -234,20 +273,24 @@ def eager_gpu_baseline(wl, st, te, am, iters=5, warmup=2):
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the unmodified reference's CPU implementation of the path on this box's host cores, same
+    config / metric / unit as the main arm.  Rank 0 alone runs and prints it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = args.workload
     _, n_tuple, n_sel, B, txt, D, dt = WORKLOADS[wl]
-    base = cpu_baseline(wl, iters=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    base = cpu_reference_steps(wl, steps=max(1, args.steps), warmup=max(0, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_sample_step"],
+        "steps": base["steps_run"], "warmup": base["warmup_run"], "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dt, "data": "synthetic",
         "config": workload_config(wl, args.gpus),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "loss": base["loss"],
+        "note": "per-GPU shard on the host cores (the reference has no multi-GPU path, README.md:47); per-unit "
+                "throughput does not depend on --gpus",
     }
     emit(line)
 
@@ -261,7 +304,7 @@ def workload_config(wl, n_gpus):
             "parallelism": f"batch-sharded dp{n_gpus}, one allreduce of 2L+2 fp64"}
 
 
-# ----------------------------------------------------------------------------- main arm
+# ----------------------------------------------------------------------------- output
 _REAL_STDOUT = None
 
 
@@ -281,6 +324,381 @@ def emit(line):
     out.flush()
 
 
+# ----------------------------------------------------------------------------- helpers of the main arm
+class Ctx:
+    """Process-wide facts of one bench run."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.dist = dist
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+        self.peak, self.peak_src = peaks()
+
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = torch.tensor(list(values), dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+
+class ApiLoop:
+    """The user's call, step after step: ``fd.distill(output, batch)`` then ``loss.backward()``.  Across batch shards
+    the token counts of the NEXT batch leave for the peers while the current step runs (``fd.prefetch_counts``, what
+    ``replay`` does as soon as it has drawn a memory batch): two mask tensors alternate so that a prefetched batch
+    is a different object from the one being consumed."""
+
+    def __init__(self, ctx, fd, leaves, masks):
+        self.ctx, self.fd, self.leaves, self.masks = ctx, fd, leaves, masks
+        self.out = Out(tuple(leaves))
+        self.i = 0
+        self.prefetch = ctx.world > 1
+
+    def prime(self):
+        if self.prefetch and self.fd.process_group is not False:
+            self.fd.prefetch_counts({"attention_mask": self.masks[self.i % 2]})
+
+    def step(self):
+        fd, i = self.fd, self.i
+        self.i += 1
+        for s in self.leaves:
+            s.grad = None
+        if self.prefetch and fd.process_group is not False:
+            fd.prefetch_counts({"attention_mask": self.masks[(i + 1) % 2]})
+        loss = fd.distill(self.out, {"attention_mask": self.masks[i % 2]})
+        loss.backward()
+        return loss
+
+    def timed(self, steps, warmup, sampler=None):
+        """(GPU ms for `steps` steps, host us per step to enqueue one, last loss)."""
+        self.prime()
+        for _ in range(warmup):
+            self.step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.ctx.sync_all()
+        cm = sampler if sampler is not None else _Null()
+        with cm:
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(steps):
+                loss = self.step()
+            e1.record()
+            host_us = (time.perf_counter() - t0) / steps * 1e6   # CPU time to enqueue one step (no sync inside)
+            self.ctx.sync_all()
+        return e0.elapsed_time(e1), host_us, loss
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def make_masks(B, txt, device, ragged=False):
+    am = torch.ones(B, txt, dtype=torch.int64, device=device)
+    if ragged:
+        for b in range(B):
+            am[b, : txt - (1 + (7 * b) % txt)] = 0       # left-padded, valid length 1 + (7 b mod txt) (SURVEY 8d)
+    return [am, am.clone()]
+
+
+def synth(n_sel, B, T, D, dtype, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    st, te = [], []
+    for _ in range(n_sel):
+        s = torch.randn(B, T, D, generator=g, device=device, dtype=torch.float32)
+        t = s + 0.1 * torch.randn(B, T, D, generator=g, device=device, dtype=torch.float32)
+        st.append(s.to(dtype))
+        te.append(t.to(dtype))
+        del s, t
+    return st, te
+
+
+def live_rows(masks, n_vis):
+    """Rows the kernels really stream: visual rows + valid text rows (padded rows are neither read nor, beyond the
+    zero fill, computed)."""
+    am = masks[0]
+    return int(am.shape[0]) * n_vis + int(am.sum())
+
+
+# ----------------------------------------------------------------------------- sharded parity (N > 1)
+def sharded_parity(ctx):
+    """the N-GPU result (loss and the concatenation of the per-rank gradients) must equal the
+    single-device result on the full concatenated batch.  One small step with per-rank ragged masks (every rank holds
+    a different number of valid text tokens, which is exactly what separates global from per-rank normalisation),
+    fp32 and bf16; the concatenated batch is recomputed on this GPU with the exchange off and, on rank 0, by the CPU
+    oracle.  Raises if a tolerance is exceeded (fp32 1e-5, bf16 2e-3)."""
+    from oracle import distill_oracle as O
+    dist, world, rank, device = ctx.dist, ctx.world, ctx.rank, ctx.device
+    L, B, txt, D = 3, 3, 8, 256
+    result = {"shape": {"layers": L, "per_rank_batch": B, "T": N_VIS + txt, "D": D}, "tolerance": {"fp32": 1e-5, "bf16": 2e-3}}
+    worst_ok = True
+    for name, dtype, tol in (("fp32", torch.float32, 1e-5), ("bf16", torch.bfloat16, 2e-3)):
+        g = torch.Generator(device="cpu").manual_seed(4321)
+        s_all = [torch.randn(world * B, N_VIS + txt, D, generator=g).to(dtype) for _ in range(L)]
+        t_all = [(s.float() + 0.3 * torch.randn(world * B, N_VIS + txt, D, generator=g)).to(dtype) for s in s_all]
+        am_all = torch.zeros(world * B, txt, dtype=torch.int64)
+        for b in range(world * B):
+            am_all[b, txt - (1 + (5 * b) % txt):] = 1
+        lo, hi = rank * B, (rank + 1) * B
+
+        def run(students, teachers, am, group):
+            fd = make_method(L)
+            fd.process_group = group
+            fd.grad_multiplier = 1.0        # compare hidden-state gradients of the GLOBAL loss (no DDP averaging here)
+            leaves = [s.to(device).requires_grad_(True) for s in students]
+            tc = [t.to(device) for t in teachers]
+            fd.past_model = lambda **kw: Out(tuple(tc))
+            loss = fd.distill(Out(tuple(leaves)), {"attention_mask": am.to(device)})
+            loss.backward()
+            return loss.detach(), [x.grad for x in leaves]
+
+        loss_s, grads_s = run([s[lo:hi] for s in s_all], [t[lo:hi] for t in t_all], am_all[lo:hi], None)
+        loss_f, grads_f = run(s_all, t_all, am_all, False)
+        torch.cuda.synchronize()
+        # gather the per-rank gradients in rank order
+        gathered = []
+        for gl in grads_s:
+            parts = [torch.empty_like(gl) for _ in range(world)]
+            dist.all_gather(parts, gl.contiguous())
+            gathered.append(torch.cat(parts, 0))
+        bits = loss_s.view(torch.int32).reshape(1)
+        every = [torch.zeros_like(bits) for _ in range(world)]
+        dist.all_gather(every, bits)
+        bitwise = all(int(e) == int(every[0]) for e in every)
+        loss_rel = abs(float(loss_s) - float(loss_f)) / abs(float(loss_f))
+        num = sum(float((a.double() - b.double()).pow(2).sum()) for a, b in zip(gathered, grads_f))
+        den = sum(float(b.double().pow(2).sum()) for b in grads_f)
+        grad_rel = (num / den) ** 0.5
+        entry = {"loss_rel": loss_rel, "grad_rel": grad_rel, "bitwise_equal_across_ranks": bitwise,
+                 "loss_sharded": float(loss_s), "loss_single_device": float(loss_f)}
+        if rank == 0:
+            cfg = O.OracleConfig(modality_strategy=RECIPE["modality"], layer_strategy=RECIPE["layer_strategy"],
+                                 gamma=RECIPE["gamma"], num_hidden_layers=L, distillation_layer=None, loss=RECIPE["loss"],
+                                 num_vision_tokens=N_VIS)
+            ref = O.forward_backward(s_all, t_all, am_all, cfg)
+            entry["oracle_loss_rel"] = abs(float(loss_s) - float(ref["loss"])) / abs(float(ref["loss"]))
+            n2 = sum(float((a.cpu().double() - r.double()).pow(2).sum()) for a, r in zip(gathered, ref["grads"]))
+            d2 = sum(float(r.double().pow(2).sum()) for r in ref["grads"][:L])
+            entry["oracle_grad_rel"] = (n2 / d2) ** 0.5
+        ok = loss_rel <= tol and grad_rel <= tol and bitwise and entry.get("oracle_loss_rel", 0.0) <= tol \
+            and entry.get("oracle_grad_rel", 0.0) <= tol
+        entry["within_tolerance"] = bool(ok)
+        worst_ok = worst_ok and ok
+        result[name] = entry
+    result["loss_rel"] = max(result["fp32"]["loss_rel"], result["bf16"]["loss_rel"])
+    result["grad_rel"] = max(result["fp32"]["grad_rel"], result["bf16"]["grad_rel"])
+    result["bitwise_equal_across_ranks"] = result["fp32"]["bitwise_equal_across_ranks"] and result["bf16"]["bitwise_equal_across_ranks"]
+    flag = torch.tensor([0 if worst_ok else 1], device=device)
+    dist.all_reduce(flag)
+    result["within_tolerance"] = int(flag) == 0
+    if int(flag) != 0:
+        if rank == 0:
+            sys.stderr.write("sharded_parity FAILED: " + json.dumps(result) + "\n")
+        raise SystemExit("bench.py: the batch-sharded step does not match the single-device step (sharded_parity)")
+    return result
+
+
+# ----------------------------------------------------------------------------- C5 sweep and other workloads
+def measure_point(ctx, n_sel, B, txt, D, dt, ragged, steps, warmup, loss="mse", kernel_level=True, graphed=True, seed=77):
+    """One shape through the public API (and at kernel level): tokens*layers/s over ALL ranks, per-GPU GB/s on the
+    3*D*e basis counting only the rows that are really streamed."""
+    from mafed_b200.distill_op import distill_backward, distill_fused
+    device, world = ctx.device, ctx.world
+    T = N_VIS + txt
+    dtype = torch_dtype(dt)
+    esize = torch.finfo(dtype).bits // 8
+    st, te = synth(n_sel, B, T, D, dtype, device, seed + ctx.rank)
+    masks = make_masks(B, txt, device, ragged)
+    fd = make_method(n_sel, loss=loss)
+    fd.past_model = lambda **kw: Out(tuple(te))
+    leaves = [s.detach().requires_grad_(True) for s in st]
+    loop = ApiLoop(ctx, fd, leaves, masks)
+    api_ms, host_us, _ = loop.timed(steps, warmup)
+    rec = {"per_gpu_batch": B, "txt": txt, "T": T, "mask": "ragged" if ragged else "all-ones"}
+    kern_ms = None
+    if kernel_level:
+        layers = list(range(n_sel))
+        coeffs, modality_kind, lang_weights = fd._tables(layers)
+        plan = fd._plan(layers, coeffs, fd.distillation_coeff, modality_kind, lang_weights)
+        grads = [torch.empty_like(s) for s in st]
+        gout = torch.ones((), dtype=torch.float32, device=device)
+        tickets = [None, None]
+
+        def kstep(i):
+            if world > 1:
+                tickets[(i + 1) % 2] = fd.prefetch_counts({"attention_mask": masks[(i + 1) % 2]})
+            out, scale, ln = distill_fused(st, te, grads, masks[i % 2], plan, group=None, ticket=tickets[i % 2])
+            distill_backward(ln, grads, scale, gout, skip_if_equals=plan.assumed_grad_out * plan.grad_multiplier,
+                             grad_out_scale=plan.grad_multiplier)
+        if world > 1:
+            tickets[0] = fd.prefetch_counts({"attention_mask": masks[0]})
+        for i in range(warmup):
+            kstep(i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.sync_all()
+        e0.record()
+        for i in range(warmup, warmup + steps):
+            kstep(i)
+        e1.record()
+        ctx.sync_all()
+        kern_ms = e0.elapsed_time(e1)
+    graph_ms, graph_host_us = None, None
+    if graphed:
+        # the same API calls captured once into a CUDA graph and replayed (mafed_b200.graphed): what the step costs a
+        # trainer that graphs its training step -- the host no longer walks Python and the autograd engine per step
+        from mafed_b200.graphed import GraphedDistillStep
+        gfd = make_method(n_sel, loss=loss)
+        gstep = GraphedDistillStep(gfd, st, te, masks[0])
+        for _ in range(warmup):
+            gstep.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.sync_all()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            gstep.replay()
+        e1.record()
+        graph_host_us = (time.perf_counter() - t0) / steps * 1e6
+        ctx.sync_all()
+        graph_ms = e0.elapsed_time(e1)
+        del gstep, gfd
+    api_ms, kern_ms_m, graph_ms_m = ctx.max_over_ranks([api_ms, kern_ms if kern_ms is not None else 0.0,
+                                                        graph_ms if graph_ms is not None else 0.0])
+    ms = api_ms / steps
+    units = B * T * n_sel * world
+    live = live_rows(masks, N_VIS) * n_sel            # rows streamed on THIS rank
+    gbs = 3 * D * esize * live / (ms * 1e-3) / 1e9
+    rec.update({"value": units / (ms * 1e-3), "ms_per_step": ms, "host_us_per_step": host_us,
+                "step_gbs_per_gpu": gbs, "frac": gbs / ctx.peak})
+    if kernel_level:
+        kms = kern_ms_m / steps
+        rec.update({"kernel_level_ms_per_step": kms, "kernel_level_value": units / (kms * 1e-3),
+                    "api_over_kernel": ms / kms})
+    if graphed:
+        gms = graph_ms_m / steps
+        rec.update({"graphed_ms_per_step": gms, "graphed_value": units / (gms * 1e-3),
+                    "graphed_host_us_per_step": graph_host_us,
+                    "graphed_frac": 3 * D * esize * live / (gms * 1e-3) / 1e9 / ctx.peak})
+        if kernel_level:
+            rec["graphed_over_kernel"] = gms / (kern_ms_m / steps)
+    del st, te, leaves, fd, loop
+    return rec
+
+
+def c5_sweep(ctx, steps=40, warmup=8):
+    """BASELINE.json configs[4] / SURVEY 8(d) row C5: VLPythia-1B distillation, 15 layers, bf16, per-GPU batch
+    8..128 (global batch 8N..128N) x text 32 / 256 (visual:text 8:1 and 1:1) x all-ones / ragged masks."""
+    points = []
+    for B in (8, 16, 32, 64, 128):
+        for txt in (32, 256):
+            for ragged in (False, True):
+                points.append(measure_point(ctx, 15, B, txt, 2048, "bf16", ragged, steps, warmup))
+    small = [p for p in points if p["per_gpu_batch"] == 8 and p["txt"] == 32 and p["mask"] == "all-ones"][0]
+    return {"what": "VLPythia-1B (D=2048, 15 distilled layers, bf16): per-GPU batch x text length x mask through "
+                    "fd.distill() + loss.backward() (`value`, `ms_per_step`; max over ranks), the same calls captured "
+                    "into a CUDA graph and replayed (`graphed_*`), and the kernel-level loop (C-ABI calls from Python, "
+                    "no autograd) beside them; GB/s per GPU on the 3*D*e basis over streamed rows",
+            "n_gpus": ctx.world, "steps": steps, "warmup": warmup, "points": points,
+            "smallest_point_api_over_kernel": small["api_over_kernel"],
+            "smallest_point_graphed_over_kernel": small.get("graphed_over_kernel")}
+
+
+def other_workloads(ctx, skip, steps=100, warmup=20):
+    """The other BASELINE.json configurations that fit one GPU, through the public API (one-pass step), plus the
+    cosine loss and fp32 hidden states at the base / 1B shapes.  Informational; the headline stays `value`."""
+    out = {}
+    rows = [("C2", WORKLOADS["C2"], "mse"), ("C3", WORKLOADS["C3"], "mse"), ("C1", WORKLOADS["C1"], "mse"),
+            ("C2_cosine", WORKLOADS["C2"], "cosine"), ("C4_cosine", WORKLOADS["C4"], "cosine"),
+            ("C2_fp32", WORKLOADS["C2"][:6] + ("fp32",), "mse"), ("C4_fp32", WORKLOADS["C4"][:6] + ("fp32",), "mse")]
+    for name, (desc, n_tuple, n_sel, B, txt, D, dt), loss in rows:
+        if name == skip:
+            continue
+        rec = measure_point(ctx, n_sel, B, txt, D, dt, False, steps, warmup, loss=loss, kernel_level=False,
+                            graphed=name in ("C1", "C2"))
+        esize = 4 if dt == "fp32" else 2
+        rec.update({"workload": desc + (f" [{loss}]" if loss != "mse" else "") + (" [fp32 hidden states]" if name.endswith("fp32") else ""),
+                    "unit": UNIT, "bytes_per_unit": 3 * D * esize,
+                    "note": "L2-assisted: student+teacher+gradient = 234 MB vs 126 MB L2" if name == "C1" else ""})
+        out[name] = rec
+    return out
+
+
+# ----------------------------------------------------------------------------- end to end with host buffers
+def run_e2e(ctx, fd, st, te, am, units_per_step):
+    """Same metric through the C ABI's host-buffer step (``mafed_host_step_run``) at every N: pinned host
+    student / teacher / mask -> device, the one-pass step per layer, gradients and losses -> pinned host, pipelined
+    over three streams inside the library; across batch shards the same call carries the communicator (counts sent
+    ahead once per step, sums exchanged per layer)."""
+    from mafed_b200.host_step import CHostStep
+    args, device, world = ctx.args, ctx.device, ctx.world
+    hs = CHostStep(fd, st, te, am, device)
+    for _ in range(2):
+        hs.step()
+    ctx.sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.e2e_steps):
+        loss = hs.step()
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    (ms,) = ctx.max_over_ranks([max(e0.elapsed_time(e1), wall_ms)])
+    ms /= args.e2e_steps
+    rec = {"value": units_per_step / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes,
+           "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": ms, "steps": args.e2e_steps,
+           "loss": float(loss), "note": hs.note,
+           "h2d_gbs_per_rank_in_step": hs.h2d_bytes / (ms * 1e-3) / 1e9, "d2h_gbs_per_rank_in_step": hs.d2h_bytes / (ms * 1e-3) / 1e9}
+    # what the host path of this box gives every rank when all ranks copy at once (the bound of the leg above)
+    try:
+        n = 1 << 30
+        hbuf = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        dbuf = torch.empty(n, dtype=torch.uint8, device=device)
+        s2 = torch.cuda.Stream(device)
+        probe = {}
+        for label in ("h2d", "d2h", "both"):
+            ctx.sync_all()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(3):
+                if label in ("h2d", "both"):
+                    dbuf.copy_(hbuf, non_blocking=True)
+                if label in ("d2h", "both"):
+                    with torch.cuda.stream(s2):
+                        hbuf2 = probe.setdefault("_h2", torch.empty(n, dtype=torch.uint8, pin_memory=True))
+                        hbuf2.copy_(dbuf, non_blocking=True)
+            torch.cuda.current_stream(device).wait_stream(s2)
+            a1.record()
+            torch.cuda.synchronize()
+            (pms,) = ctx.max_over_ranks([a0.elapsed_time(a1)])
+            probe[label + "_gbs_per_rank"] = 3 * n / (pms * 1e-3) / 1e9
+        probe.pop("_h2", None)
+        probe["note"] = "1 GiB pinned copies, all ranks at once, slowest rank; 'both' = each direction while the other runs"
+        rec["pcie_probe"] = probe
+        h2d, d2h = probe["both_gbs_per_rank"], probe["both_gbs_per_rank"]
+        rec["pcie_bound_ms"] = max(hs.h2d_bytes / (h2d * 1e9), hs.d2h_bytes / (d2h * 1e9)) * 1e3
+    except Exception as exc:   # the probe is informational
+        rec["pcie_probe"] = {"error": repr(exc)}
+    hs.close()
+    return rec
+
+
+# ----------------------------------------------------------------------------- main arm
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -293,6 +711,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-workloads", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
@@ -302,58 +721,60 @@ def main():
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                                    str(29000 + os.getpid() % 2000), os.path.abspath(__file__), *sys.argv[1:]])
     if args.impl == "reference":
-        if args.steps > 5:
-            args.steps = 5
         return run_reference_arm(args)
     if args.warmup < 3:
         args.warmup = 3
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the distillation path has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    n_gpus = world
+    ctx = Ctx(args)
+    world, rank, device, dist = ctx.world, ctx.rank, ctx.device, ctx.dist
 
-    from mafed_b200 import build, cabi
+    from mafed_b200 import build, cabi, node
     if rank == 0:
         build.build()
+        build.build_torch_ext()
     if world > 1:
         dist.barrier()
-    lib = cabi.load()
-    from mafed_b200.distill_op import distill_backward, distill_forward
+    cabi.load()
+    node.load()
+    variant = {"default": 0, "ldg": 1, "tma": 2}[args.variant]
+    with cabi.tuning(variant=variant) if variant else _Null():
+        line = run_main(ctx)
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_main(ctx):
+    from mafed_b200.distill_op import distill_backward, distill_forward, distill_fused
+    args, world, rank, device, dist = ctx.args, ctx.world, ctx.rank, ctx.device, ctx.dist
+    peak, peak_src = ctx.peak, ctx.peak_src
+    parity = sharded_parity(ctx) if world > 1 else None     # before anything is timed; fails the run if wrong
 
     wl = args.workload
     desc, n_tuple, n_sel, B, txt, D, dt = WORKLOADS[wl]
     T = N_VIS + txt
     esize = torch.finfo(torch_dtype(dt)).bits // 8
     st, te, am = make_device_inputs(wl, rank, device)
+    masks = [am, am.clone()]
     fd = make_method(n_sel)
     fd.populate_batch_masks = True
     fd.past_model = lambda **kw: Out(tuple(te))
     leaves = [s.detach().requires_grad_(True) for s in st]
-    units_per_step = B * T * n_sel * n_gpus
-
-    def api_step():
-        """The call a user makes: FeatureDistillation.distill(...) then loss.backward()."""
-        for s in leaves:
-            s.grad = None
-        loss = fd.distill(Out(tuple(leaves)), {"attention_mask": am})
-        loss.backward()
-        return loss
+    units_per_step = B * T * n_sel * world
+    loop = ApiLoop(ctx, fd, leaves, masks)
 
     # ---- (1) kernel-level steps with per-stage events (for the roofline of each kernel)
-    from mafed_b200.distill_op import distill_fused
     layers = list(range(n_sel))
     coeffs, modality_kind, lang_weights = fd._tables(layers)
     plan = fd._plan(layers, coeffs, fd.distillation_coeff, modality_kind, lang_weights)
     grads = [torch.empty_like(s) for s in st]
     gout = torch.ones((), dtype=torch.float32, device=device)
+    fixed = plan.assumed_grad_out * plan.grad_multiplier
+    tickets = [None, None]
+    counter = [0]
 
     def two_pass_step(ev=None):
         if ev:
@@ -361,52 +782,31 @@ def main():
         out, scale, ln = distill_forward(st, te, am, plan, group=None)      # fwd kernel (losses in its last CTA)
         if ev:
             ev[1].record()
-        distill_backward(ln, grads, scale, gout)                            # bwd kernel
+        distill_backward(ln, grads, scale, gout, grad_out_scale=plan.grad_multiplier)   # bwd kernel
         if ev:
             ev[2].record()
         return out
 
     def one_pass_step(ev=None):
+        i = counter[0]
+        counter[0] += 1
+        if world > 1:
+            tickets[(i + 1) % 2] = fd.prefetch_counts({"attention_mask": masks[(i + 1) % 2]})
         if ev:
             ev[0].record()
-        out, scale, ln = distill_fused(st, te, grads, am, plan, group=None)  # the whole step: one launch
+        out, scale, ln = distill_fused(st, te, grads, masks[i % 2], plan, group=None, ticket=tickets[i % 2])  # the whole step
         if ev:
             ev[1].record()
-        distill_backward(ln, grads, scale, gout, skip_if_equals=plan.assumed_grad_out)  # the gate: returns at once
+        distill_backward(ln, grads, scale, gout, skip_if_equals=fixed, grad_out_scale=plan.grad_multiplier)   # the gate
         if ev:
             ev[2].record()
         return out
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    host_us = {}
-    peer, trace_marks = None, []
+    peer = None
     if world > 1:
         from mafed_b200.comm import get_peer_comm
         peer = get_peer_comm(None)
-
-    def api_loop(single_pass):
-        fd.single_pass = single_pass
-        for _ in range(args.warmup):
-            api_step()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(local_rank)
-        sync_all()
-        if single_pass and peer is not None:
-            trace_marks.append(peer.trace())     # exchange cycles before the timed steps (warm-up excluded)
-        with sampler:
-            t0 = time.perf_counter()
-            e0.record()
-            for _ in range(args.steps):
-                loss = api_step()
-            e1.record()
-            host_us[single_pass] = (time.perf_counter() - t0) / args.steps * 1e6   # CPU time to enqueue one step
-            sync_all()
-        return e0.elapsed_time(e1), sampler, loss
+        tickets[0] = fd.prefetch_counts({"attention_mask": masks[0]})
 
     step_stats = {}
 
@@ -414,10 +814,10 @@ def main():
         for _ in range(args.warmup):
             step_fn()
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-        sync_all()
+        ctx.sync_all()
         for i in range(args.steps):
             step_fn(evs[i])
-        sync_all()
+        ctx.sync_all()
         a = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
         b = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
         per_step = [e[0].elapsed_time(e[2]) for e in evs]
@@ -425,35 +825,32 @@ def main():
         return a, b, evs[0][0].elapsed_time(evs[-1][2])
 
     fwd_ms, bwd_ms, two_raw_ms = stage_loop(two_pass_step)
-    fused_ms, fixup_ms, one_raw_ms = stage_loop(one_pass_step)
-    two_api_ms, _, _ = api_loop(False)
-    api_ms, sampler, loss = api_loop(True)          # the product default: the headline `value`
-    trace0 = trace_marks[-1] if trace_marks else None
+    fused_ms, gate_ms, one_raw_ms = stage_loop(one_pass_step)
+
+    # ---- (2) the public API: the headline `value`
+    fd.single_pass = False
+    two_api_ms, _, _ = loop.timed(args.steps, args.warmup)
+    fd.single_pass = True
+    trace0 = peer.trace() if peer is not None else None
+    sampler = ClockSampler(ctx.local_rank)
+    api_ms, host_us, loss = loop.timed(args.steps, args.warmup, sampler)
     trace1 = peer.trace() if peer is not None else None
     uncoupled = None
     if world > 1:
-        # the same API step with the exchange switched off (per-rank loss), all ranks at once: what every GPU does
-        # on its own.  The coupled step cannot be faster than the slowest of these.
+        # the same API step with the exchange switched off (per-rank loss), all ranks at once: what every GPU does on
+        # its own.  The coupled step cannot be faster than the slowest of these.
         fd.process_group = False
-        own_ms, _, _ = api_loop(True)
+        own_ms, _, _ = loop.timed(args.steps, args.warmup)
         fd.process_group = None
         own = torch.tensor([own_ms / args.steps], dtype=torch.float64, device=device)
         every = [torch.zeros_like(own) for _ in range(world)]
         dist.all_gather(every, own)
         uncoupled = [float(x) for x in every]
-    t = torch.tensor([api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, fixup_ms],
-                     dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, fixup_ms = t.tolist()
+    api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms = ctx.max_over_ranks(
+        [api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms])
     ms_per_step = api_ms / args.steps
     value = units_per_step / (ms_per_step * 1e-3)
 
-    peak, peak_src = peaks()
-    peer_path = False
-    if world > 1:
-        from mafed_b200.comm import get_peer_comm
-        peer_path = get_peer_comm(None) is not None
     row_bytes = D * esize
     per_gpu_units = B * T * n_sel
     gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9
@@ -461,26 +858,29 @@ def main():
     bwd_bytes = 3 * row_bytes * per_gpu_units
     fwd_bytes = 2 * row_bytes * per_gpu_units
     two_ms = two_api_ms / args.steps
+    launches_per_step = 2 if world == 1 else (3 if peer is not None else 8)
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dt,
-        "data": "synthetic", "config": workload_config(wl, n_gpus),
+        "data": "synthetic", "config": workload_config(wl, world),
         "arithmetic": f"{dt} hidden states widened exactly to fp32; fp32 accumulation, fp64 final reduction; "
                       f"gradients rounded once to {dt}",
         "mode": "one-pass (loss sums + gradients from a single read of student and teacher; 3*D*e bytes per "
-                "token*layer; upstream gradient checked on the device in backward)",
+                "token*layer; upstream gradient checked on the device by a 1-CTA gate in backward)",
+        "api": "FeatureDistillation.distill(output, batch) + loss.backward(): one call into the compiled autograd node "
+               "(csrc/torch_node.cpp) per direction",
         "roofline": {"bound": "hbm", "kernel": "k_bwd_tma<kFused> (whole step: masks, scale table, sums, gradients, losses): "
                                                 "2 reads + 1 write",
                      "achieved": gbs(fused_bytes, fused_ms), "peak": peak, "unit": "GB/s",
                      "frac": gbs(fused_bytes, fused_ms) / peak, "traffic": measured_traffic(wl), "peak_source": peak_src,
                      "bytes_per_launch": fused_bytes, "bytes_per_unit": 3 * row_bytes, "ms_per_launch": fused_ms,
-                     "fixup_launch_ms": fixup_ms},
+                     "gate_launch_ms": gate_ms, "fixup_launch_ms": gate_ms},
         "roofline_step": {"achieved": gbs(fused_bytes, ms_per_step), "peak": peak, "unit": "GB/s",
                           "frac": gbs(fused_bytes, ms_per_step) / peak,
                           "frac_of_nominal_8000": gbs(fused_bytes, ms_per_step) / 8000.0, "bytes_per_unit": 3 * row_bytes},
         "kernel_value": units_per_step / (one_raw_ms / args.steps * 1e-3),
-        "host_us_per_step": host_us.get(True),
+        "host_us_per_step": host_us,
         "kernel_level_step_ms": {"one_pass": step_stats.get("one_pass_step"), "two_pass": step_stats.get("two_pass_step")},
         "two_pass": {
             "note": "north_star's two-kernel form (fused forward, then fused backward): 5*D*e bytes per token*layer",
@@ -497,13 +897,17 @@ def main():
                               "bytes_per_unit": 5 * row_bytes},
         },
         # per step: the fused kernel (modality masks, scale table, loss sums + gradients, and the loss algebra in its
-        # last CTA) and the backward fix-up; batch-sharded over peer memory: the same two (both exchanges inside the
-        # fused kernel); NCCL fallback: masks, counts, prologue, fused, reduce, finalize, fix-up
-        "gpu_launches": args.steps * (2 if (world == 1 or peer_path) else 7),
-        "exchange": "none" if world == 1 else ("nvlink peer-memory mailboxes inside the fused kernel: counts at its start, "
-                                               "sums in its last CTA" if peer_path else "nccl allreduce"),
+        # last CTA) and the 1-CTA backward gate; batch-sharded over peer memory: those two plus the 1-CTA count
+        # prefetch of the next batch; NCCL sequence: masks, counts, scale, fused, reduce, finalize, gate + 2 allreduces
+        "gpu_launches": args.steps * launches_per_step,
+        "exchange": "none" if world == 1 else (
+            "nvlink peer-memory mailboxes: token counts sent ahead of the step by a 1-CTA launch when the batch is drawn "
+            "(the fused kernel reads them from its own mailbox), sums exchanged by the fused kernel's last CTA"
+            if peer is not None else "nccl allreduce"),
         "loss": float(loss.detach()),
     }
+    if parity is not None:
+        line["sharded_parity"] = parity
     if trace0 is not None:
         # SM cycles the in-kernel exchanges took on rank 0 (mafed_comm_trace), per step, in us at the sampled SM clock
         mhz = float(sampler.summary().get("sm_mhz") or 1900.0)
@@ -512,23 +916,29 @@ def main():
             "counts_exchange_in_fused_kernel": (trace1[0] - trace0[0]) / calls / mhz,
             "sums_publish_in_tail": (trace1[1] - trace0[1]) / calls / mhz,
             "sums_wait_for_peers_in_tail": (trace1[2] - trace0[2]) / calls / mhz,
-            "steps_traced": calls}
+            "steps_traced": calls, "includes_warmup": True}
     if uncoupled is not None:
         line["uncoupled_ms_per_rank"] = uncoupled
+        line["coupling_cost_us"] = (ms_per_step - max(uncoupled)) * 1e3
         line["uncoupled_note"] = ("API step with the exchange off, all ranks running at once; the coupled step waits for "
                                   "the slowest GPU every step: ms_per_step vs max(uncoupled) is the cost of the exchange "
                                   "itself, max(uncoupled) vs the 1-GPU run is GPU-to-GPU variation")
     line["clocks"] = sampler.summary()
 
-    # ---- (2) end to end with HOST buffers (pinned): H2D inputs, step, D2H gradients + loss
+    if not args.no_c5:
+        try:
+            line["c5"] = c5_sweep(ctx)
+        except Exception as exc:
+            line["c5"] = {"error": repr(exc)}
     if world == 1 and not args.no_other_workloads:
         try:
-            line["other_workloads"] = other_workloads(wl, device, peak)
+            line["other_workloads"] = other_workloads(ctx, wl)
         except Exception as exc:
             line["other_workloads"] = {"error": repr(exc)}
+    # ---- (3) end to end with HOST buffers (pinned): H2D inputs, step, D2H gradients + loss
     if not args.no_e2e:
         try:
-            line["e2e"] = run_e2e(args, fd, st, te, am, device, world, units_per_step)
+            line["e2e"] = run_e2e(ctx, fd, st, te, am, units_per_step)
         except Exception as exc:  # keep the headline line even if the host path cannot allocate
             line["e2e"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
@@ -538,86 +948,11 @@ def main():
             line["eager_torch_gpu"] = {"error": repr(exc)}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
-            base = cpu_baseline(wl)
+            base = cpu_reference_steps(wl, steps=3, warmup=1, budget_s=60.0)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as exc:
             line["cpu_baseline"] = {"error": repr(exc)}
-    if rank == 0:
-        emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-
-
-def other_workloads(skip, device, peak, steps=100, warmup=20):
-    """The other BASELINE.json configurations that fit one GPU, through the public API (one-pass step):
-    tokens*layers/s and the step's algorithmic GB/s.  Informational; the headline stays `value`."""
-    out = {}
-    for wl in ("C2", "C3", "C1"):
-        if wl == skip:
-            continue
-        desc, n_tuple, n_sel, B, txt, D, dt = WORKLOADS[wl]
-        st, te, am = make_device_inputs(wl, 0, device)
-        fd = make_method(n_sel)
-        fd.past_model = lambda **kw: Out(tuple(te))
-        leaves = [s.detach().requires_grad_(True) for s in st]
-
-        def step():
-            for s in leaves:
-                s.grad = None
-            loss = fd.distill(Out(tuple(leaves)), {"attention_mask": am})
-            loss.backward()
-
-        for _ in range(warmup):
-            step()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(steps):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
-        units = B * (N_VIS + txt) * n_sel
-        esize = torch.finfo(torch_dtype(dt)).bits // 8
-        gbs = 3 * D * esize * units / (ms * 1e-3) / 1e9
-        out[wl] = {"workload": desc, "value": units / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "step_gbs": gbs,
-                   "frac": gbs / peak, "bytes_per_unit": 3 * D * esize,
-                   "note": "L2-assisted: student+teacher+gradient = 234 MB vs 126 MB L2" if wl == "C1" else ""}
-        del st, te, leaves, fd
-    return out
-
-
-def run_e2e(args, fd, st, te, am, device, world, units_per_step):
-    """Same metric through the public API with host-resident inputs and outputs.
-
-    Every step: pinned host student/teacher/mask -> device (H2D), distill + backward, gradients and the
-    loss -> pinned host (D2H).  Layers are pipelined over three streams so copies overlap the kernels.
-    """
-    import torch.distributed as dist
-    from mafed_b200.host_step import CHostStep, HostStep
-    # single GPU: the C ABI's own host-buffer entry (mafed_host_step_run); batch-sharded runs use the Python
-    # pipeline over the same kernels because it carries the cross-rank exchange
-    hs = (CHostStep if world == 1 else HostStep)(fd, st, te, am, device)
-    for _ in range(2):
-        hs.step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.e2e_steps):
-        loss = hs.step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t) / args.e2e_steps
-    return {"value": units_per_step / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes,
-            "d2h_bytes_per_step": hs.d2h_bytes, "ms_per_step": ms, "steps": args.e2e_steps,
-            "loss": float(loss), "note": hs.note}
+    return line
 
 
 if __name__ == "__main__":

@@ -216,14 +216,15 @@ struct DistillBackward : public Node {
 
 // ---------------------------------------------------------------- forward
 // students / teachers: the selected [B, T, D] hidden states (same dtype, shape, device).  attn_mask: int64 [B, T - n_vis]
-// (ignored in cls mode).  masks_out: optional int64 [2, B, T] that receives (lang_masks, image_masks).  comm: a
-// mafed_comm_t* (0: single rank).  ticket: optional int64[4] from prefetch_counts.  seen: optional pinned float[1].
-// Returns (total, aux): the 0-dim fp32 loss with the node attached, and the [3L] layer / (text, vision) losses.
-std::tuple<at::Tensor, at::Tensor> distill(const std::shared_ptr<Plan>& plan, std::vector<at::Tensor> students,
-                                           std::vector<at::Tensor> teachers, const c10::optional<at::Tensor>& attn_mask,
-                                           const c10::optional<at::Tensor>& masks_out, int64_t comm,
-                                           const c10::optional<at::Tensor>& ticket,
-                                           const c10::optional<at::Tensor>& seen, int64_t tuning_addr) {
+// (ignored in cls mode).  masks_out: None, an int64 [2, B, T] tensor, or True to have one allocated here; it receives
+// (lang_masks, image_masks).  comm: a mafed_comm_t* (0: single rank).  ticket: optional int64[4] from
+// prefetch_counts.  seen: optional pinned float[1].
+// Returns (total, aux, masks): the 0-dim fp32 loss with the node attached, the [3L] layer / (text, vision) losses,
+// and the [2, B, T] mask tensor (None if not requested).
+std::tuple<at::Tensor, at::Tensor, c10::optional<at::Tensor>> distill(
+    const std::shared_ptr<Plan>& plan, std::vector<at::Tensor> students, std::vector<at::Tensor> teachers,
+    const c10::optional<at::Tensor>& attn_mask, const py::object& masks_out, int64_t comm,
+    const c10::optional<at::Tensor>& ticket, const c10::optional<at::Tensor>& seen, int64_t tuning_addr) {
   const Api& a = api();
   const int L = plan->n_layers;
   TORCH_CHECK((int)students.size() == L && (int)teachers.size() == L, "students / teachers / plan length mismatch");
@@ -316,13 +317,21 @@ std::tuple<at::Tensor, at::Tensor> distill(const std::shared_ptr<Plan>& plan, st
   }
   int64_t* lang = nullptr;
   int64_t* image = nullptr;
-  if (masks_out.has_value() && masks_out->defined() && !plan->cls) {
-    const at::Tensor& mo = *masks_out;
-    TORCH_CHECK_VALUE(mo.is_cuda() && mo.scalar_type() == at::kLong && mo.is_contiguous() && mo.dim() == 3 &&
-                          mo.size(0) == 2 && mo.size(1) == B && mo.size(2) == T,
-                      "masks_out must be a contiguous int64 [2, B, T] CUDA tensor");
-    lang = mo.data_ptr<int64_t>();
-    image = lang + B * T;
+  c10::optional<at::Tensor> masks;
+  if (!masks_out.is_none() && !plan->cls) {
+    if (py::isinstance<py::bool_>(masks_out)) {
+      if (masks_out.cast<bool>()) masks = at::empty({2, B, T}, at::TensorOptions().dtype(at::kLong).device(device));
+    } else {
+      masks = masks_out.cast<at::Tensor>();
+    }
+    if (masks.has_value()) {
+      const at::Tensor& mo = *masks;
+      TORCH_CHECK_VALUE(mo.is_cuda() && mo.scalar_type() == at::kLong && mo.is_contiguous() && mo.dim() == 3 &&
+                            mo.size(0) == 2 && mo.size(1) == B && mo.size(2) == T,
+                        "masks_out must be a contiguous int64 [2, B, T] CUDA tensor");
+      lang = mo.data_ptr<int64_t>();
+      image = lang + B * T;
+    }
   }
   const int64_t* mask_ptr = mask.defined() ? mask.data_ptr<int64_t>() : nullptr;
   const int64_t* ticket_ptr = nullptr;
@@ -383,7 +392,7 @@ std::tuple<at::Tensor, at::Tensor> distill(const std::shared_ptr<Plan>& plan, st
     }
     torch::autograd::set_history(total, node);
   }
-  return std::make_tuple(std::move(total), std::move(aux));
+  return std::make_tuple(std::move(total), std::move(aux), std::move(masks));
 }
 
 // Token counts ahead of the step (mafed_distill_prefetch_counts): returns the int64[4] ticket.

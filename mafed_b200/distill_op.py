@@ -445,23 +445,30 @@ def _step(plan: DistillPlan, attn_mask, group, teachers, mask_out, students, tic
     distributed, pg = resolve_group(group)
     peer = get_peer_comm(pg) if distributed else None
     if distributed and peer is None:
+        if mask_out is True:
+            mask_out = torch.empty((2, attn_mask.shape[0], plan.n_vis + attn_mask.shape[1]), dtype=torch.int64,
+                                   device=attn_mask.device)
         both = (mask_out[0], mask_out[1]) if mask_out is not None else None
         if len({t.dtype for t in students} | {t.dtype for t in teachers}) > 1:
             students, teachers = [s.float() for s in students], [t.float() for t in teachers]
-        return _DistillFunction.apply(plan, attn_mask, group, tuple(_prepare(teachers)), both, *students)
+        total, aux = _DistillFunction.apply(plan, attn_mask, group, tuple(_prepare(teachers)), both, *students)
+        return total, aux, mask_out
     ext = node.load()
     return ext.distill(plan.node_plan(), students, teachers, None if plan.cls else attn_mask, mask_out,
                        peer.handle.value if peer is not None else 0, ticket, seen, cabi.active_tuning_address())
 
 
 def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tensor], attn_mask, plan: DistillPlan,
-                 group=None, teachers_detached: bool = False, mask_out=None, ticket=None, seen=None):
+                 group=None, teachers_detached: bool = False, mask_out=None, ticket=None, seen=None,
+                 return_masks: bool = False):
     """Differentiable fused distillation loss over ``len(students)`` selected layers.
 
     Returns ``(total, aux)``: ``total`` is the 0-dim fp32 loss (gradients flow to ``students``),
     ``aux`` the non-differentiable ``[3L]`` vector of layer losses then (text, vision) losses.
-    ``mask_out``: optional pre-allocated int64 ``[2, B, T]`` tensor; the step's own kernel fills ``[0]`` with
-    ``lang_masks`` and ``[1]`` with ``image_masks`` (``attn_mask`` must then be a contiguous int64 CUDA tensor).
+    ``mask_out``: optional pre-allocated int64 ``[2, B, T]`` tensor, or ``True`` to have one allocated; the step's
+    own kernel fills ``[0]`` with ``lang_masks`` and ``[1]`` with ``image_masks`` (``attn_mask`` must then be a
+    contiguous int64 CUDA tensor); ``return_masks=True`` appends ``(lang_masks, image_masks)`` (or ``None``) to
+    the result.
     ``ticket``: the token counts sent ahead of the step (``prefetch_counts``).  ``seen``: pinned float32 tensor
     that receives the upstream gradient the backward gate saw.
     """
@@ -473,9 +480,12 @@ def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tens
     # distillation.py:90,244)
     n = len(students)
     if n <= cabi.MAX_LAYERS:
-        return _step(plan, attn_mask, group, teachers, mask_out, students, ticket, seen)
+        total, aux, both = _step(plan, attn_mask, group, teachers, mask_out, students, ticket, seen)
+        if not return_masks:
+            return total, aux
+        return total, aux, (None if both is None else (both[0], both[1]))
     # more selected layers than one launch carries (MAFED_MAX_LAYERS): chunk and add the partial totals
-    total, layer_losses, modal_losses = None, [], []
+    total, layer_losses, modal_losses, both = None, [], [], None
     for lo in range(0, n, cabi.MAX_LAYERS):
         hi = min(n, lo + cabi.MAX_LAYERS)
         sub = DistillPlan(layers=plan.layers[lo:hi], layer_coeffs=plan.layer_coeffs[lo:hi],
@@ -484,9 +494,14 @@ def distill_loss(students: Sequence[torch.Tensor], teachers: Sequence[torch.Tens
                           loss_kind=plan.loss_kind, cls=plan.cls, n_vis=plan.n_vis,
                           grad_multiplier=plan.grad_multiplier, single_pass=plan.single_pass,
                           assumed_grad_out=plan.assumed_grad_out)
-        part, aux = _step(sub, attn_mask, group, teachers[lo:hi], mask_out if lo == 0 else None, students[lo:hi],
-                          ticket, seen)
+        part, aux, masks = _step(sub, attn_mask, group, teachers[lo:hi], mask_out if lo == 0 else None,
+                                 students[lo:hi], ticket, seen)
+        if lo == 0:
+            both = masks
         total = part if total is None else total + part
         layer_losses.append(aux[: hi - lo])
         modal_losses.append(aux[hi - lo:])
-    return total, torch.cat(layer_losses + modal_losses)
+    aux = torch.cat(layer_losses + modal_losses)
+    if not return_masks:
+        return total, aux
+    return total, aux, (None if both is None else (both[0], both[1]))

@@ -231,14 +231,16 @@ class FeatureDistillation(CLStrategy):
     def distill(self, output, batch):
         """Sum over the selected layers of ``layer_coeff * distillation_coeff * layer_loss``
         (``distillation.py:105-122``) -- as one fused launch instead of a Python loop."""
-        past_hidden_states = self._get_past_hidden_states(batch)
         layers = self.loss_weights.get_distillation_layers()
+        # the teacher's states come out of a no_grad forward and the node never differentiates them: the per-tensor
+        # `.detach()` of the reference (`_get_past_hidden_states`, distillation.py:223) is only paid for the distilled
+        # layers, and only if a tensor carries a graph at all
+        past_hidden_states = self._past_states(batch, layers)
         if self.adapt_assumed_grad_out and self._gout_seen_np is not None:
             self._adapt_assumed()
         plan = self._step_plan(layers)
         hidden = output.hidden_states
-        total, aux = self._launch(plan, batch, [hidden[l] for l in layers], [past_hidden_states[l] for l in layers],
-                                  teachers_detached=True)
+        total, aux = self._launch(plan, batch, [hidden[l] for l in layers], past_hidden_states, teachers_detached=True)
         self._record(aux, layers)
         self.step += 1
         return total
@@ -312,10 +314,8 @@ class FeatureDistillation(CLStrategy):
             attn = batch["attention_mask"]
             if self.populate_batch_masks:
                 if attn.is_cuda and attn.dtype == torch.int64 and attn.is_contiguous():
-                    # the masks the reference leaves in `batch` are written by the step's own kernel
-                    mask_out = torch.empty((2, attn.shape[0], self.num_vision_tokens + attn.shape[1]),
-                                           dtype=torch.int64, device=attn.device)
-                    batch["lang_masks"], batch["image_masks"] = mask_out[0], mask_out[1]
+                    # the masks the reference leaves in `batch` are allocated and written by the step itself
+                    mask_out = True
                 else:
                     batch["lang_masks"], batch["image_masks"] = modality_masks(attn, self.num_vision_tokens)
             tk = self._ticket
@@ -326,9 +326,26 @@ class FeatureDistillation(CLStrategy):
         if plan.single_pass and self._gout_seen is None:
             self._gout_seen = seen_slot()
             self._gout_seen_np = self._gout_seen.numpy()
-        return distill_loss(students, teachers, attn, plan, group=self.process_group,
-                            teachers_detached=teachers_detached, mask_out=mask_out, ticket=ticket,
-                            seen=self._gout_seen if plan.single_pass else None)
+        total, aux, masks = distill_loss(students, teachers, attn, plan, group=self.process_group,
+                                         teachers_detached=teachers_detached, mask_out=mask_out, ticket=ticket,
+                                         seen=self._gout_seen if plan.single_pass else None, return_masks=True)
+        if masks is not None:
+            batch["lang_masks"], batch["image_masks"] = masks
+        return total, aux
+
+    def _past_states(self, batch, layers):
+        """Teacher hidden states of the distilled layers only (same forward and side effects as
+        ``_get_past_hidden_states``)."""
+        with torch.no_grad():
+            batch.pop("labels", None)
+            if self.selective_capture:
+                with HiddenStateCapture(self.past_model, layers, detach=True) as cap:
+                    self.past_model(**batch, output_hidden_states=False, return_dict=True)
+                states = cap.hidden_states
+            else:
+                states = self.past_model(**batch, output_hidden_states=True, return_dict=True).hidden_states
+        return [states[l] if states[l].grad_fn is None and not states[l].requires_grad else states[l].detach()
+                for l in layers]
 
     def _get_past_hidden_states(self, batch):
         with torch.no_grad():
@@ -375,6 +392,8 @@ class FeatureDistillation(CLStrategy):
         self.check_exchange(sync=False)
         if _wandb is None or getattr(_wandb, "run", None) is None:
             return
+        if torch.cuda.is_current_stream_capturing():
+            return      # inside a CUDA-graph capture: the values stay in `last_layer_losses` (static per replay)
         self.flush_logs(wait=False)
         host = torch.empty(len(layers), dtype=torch.float32, pin_memory=True)
         host.copy_(aux[: len(layers)], non_blocking=True)

@@ -16,7 +16,10 @@ def test_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"].startswith("distill fwd+bwd") and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the arm times the UNMODIFIED reference (oracle/_ref, or /root/reference in the build container) at the full shard
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "B=8 of 8 samples" in d["cpu_baseline"]["sample"] and "unmodified reference" in d["cpu_baseline"]["sample"]
+    assert d["steps"] == 1 and d["warmup"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] and "model" not in d["config"] and d["vs_baseline"] is None
 

@@ -358,7 +358,7 @@ def test_wandb_values_are_logged_late_without_host_sync(monkeypatch):
     for l in range(3):
         assert logged[l][f"task_2/distill_loss_{l}"] == pytest.approx(float(ref["layer_losses"][l]), rel=1e-5)
     fd.flush_logs()
-    assert len(logged) == 6 and [list(d.values()) for d in logged[3:]] == pytest.approx([list(d.values()) for d in logged[:3]])
+    assert len(logged) == 6 and [v for d in logged[3:] for v in d.values()] == pytest.approx([v for d in logged[:3] for v in d.values()])
     fd.flush_logs()
     assert len(logged) == 6
     # every step is logged even when the host runs ahead of the device (values used to be dropped)
