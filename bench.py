@@ -668,7 +668,9 @@ def run_e2e(ctx, fd, st, te, am, units_per_step):
     try:
         n = 1 << 30
         hbuf = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        hbuf2 = torch.empty(n, dtype=torch.uint8, pin_memory=True)
         dbuf = torch.empty(n, dtype=torch.uint8, device=device)
+        dbuf2 = torch.empty(n, dtype=torch.uint8, device=device)
         s2 = torch.cuda.Stream(device)
         probe = {}
         for label in ("h2d", "d2h", "both"):
@@ -680,14 +682,12 @@ def run_e2e(ctx, fd, st, te, am, units_per_step):
                     dbuf.copy_(hbuf, non_blocking=True)
                 if label in ("d2h", "both"):
                     with torch.cuda.stream(s2):
-                        hbuf2 = probe.setdefault("_h2", torch.empty(n, dtype=torch.uint8, pin_memory=True))
-                        hbuf2.copy_(dbuf, non_blocking=True)
+                        hbuf2.copy_(dbuf2, non_blocking=True)
             torch.cuda.current_stream(device).wait_stream(s2)
             a1.record()
             torch.cuda.synchronize()
             (pms,) = ctx.max_over_ranks([a0.elapsed_time(a1)])
             probe[label + "_gbs_per_rank"] = 3 * n / (pms * 1e-3) / 1e9
-        probe.pop("_h2", None)
         probe["note"] = "1 GiB pinned copies, all ranks at once, slowest rank; 'both' = each direction while the other runs"
         rec["pcie_probe"] = probe
         h2d, d2h = probe["both_gbs_per_rank"], probe["both_gbs_per_rank"]

@@ -227,13 +227,15 @@ int mafed_distill_modality_masks(const mafed_shape_t* shape, const int64_t* attn
  *         three streams; returns when gradients (h_grad[l], student dtype) and h_out[1+3L] = {total, layer
  *         losses, (text, vision) losses} are in host memory.  `grad_out` is the upstream gradient (host
  *         value).  Host buffers should be pinned (mafed_host_register) for full PCIe bandwidth.
- * Same results as mafed_distill_fused + mafed_distill_epilogue on device-resident tensors. */
+ *         With `comm` the step is batch-sharded: the counts are sent ahead once (mafed_distill_prefetch_counts,
+ *         right after the mask copy) and every layer's launch exchanges its sums with the peers.
+ * Same results as mafed_distill_step on device-resident tensors. */
 typedef struct mafed_host_step mafed_host_step_t;
 size_t mafed_host_step_device_bytes(const mafed_shape_t* shape);
 int mafed_host_step_create(const mafed_shape_t* shape, mafed_host_step_t** out);
 int mafed_host_step_run(mafed_host_step_t* step, const mafed_weights_t* weights, const void* const* h_student,
                         const void* const* h_teacher, void* const* h_grad, const int64_t* h_mask, float grad_out,
-                        float* h_out);
+                        float* h_out, mafed_comm_t* comm /* NULL: single rank */);
 int mafed_host_step_destroy(mafed_host_step_t* step);
 int mafed_host_register(void* ptr, size_t bytes);
 int mafed_host_unregister(void* ptr);

@@ -164,7 +164,7 @@ def load():
         lib.mafed_host_step_create.restype = i32
         lib.mafed_host_step_create.argtypes = [sh, ctypes.POINTER(vp)]
         lib.mafed_host_step_run.restype = i32
-        lib.mafed_host_step_run.argtypes = [vp, wt, pp, pp, pp, vp, ctypes.c_float, vp]
+        lib.mafed_host_step_run.argtypes = [vp, wt, pp, pp, pp, vp, ctypes.c_float, vp, vp]
         lib.mafed_host_step_destroy.restype = i32
         lib.mafed_host_step_destroy.argtypes = [vp]
         lib.mafed_host_register.restype = i32

@@ -470,7 +470,7 @@ size_t mafed_host_step_device_bytes(const mafed_shape_t* shape) {
   if (check_shape(shape)) return 0;
   const size_t layer = (size_t)shape->B * shape->T * shape->D * elem_size(shape->dtype);
   const size_t mask = needs_mask(*shape) ? (size_t)shape->B * (shape->T - shape->n_vis) * sizeof(int64_t) : 0;
-  return 3 * layer * shape->n_layers + mask + (size_t)shape->n_layers * (mafed_distill_ws_bytes(1) + 64) + 4096;
+  return 3 * layer * shape->n_layers + mask + (size_t)shape->n_layers * (mafed_distill_ws_bytes(1) + 128) + 4096;
 }
 
 int mafed_host_step_create(const mafed_shape_t* shape, mafed_host_step_t** out) {
@@ -484,7 +484,8 @@ int mafed_host_step_create(const mafed_shape_t* shape, mafed_host_step_t** out) 
   h->layer_bytes = (((size_t)shape->B * shape->T * shape->D * elem_size(shape->dtype)) + 255) & ~(size_t)255;
   h->mask_bytes = ((needs_mask(*shape) ? (size_t)shape->B * (shape->T - shape->n_vis) * sizeof(int64_t) : 0) + 255) & ~(size_t)255;
   h->ws_bytes = (mafed_distill_ws_bytes(1) + 255) & ~(size_t)255;
-  const size_t total = 3 * h->layer_bytes * L + h->mask_bytes + (size_t)L * h->ws_bytes + (size_t)L * 6 * sizeof(float) + 1024;
+  const size_t total = 3 * h->layer_bytes * L + h->mask_bytes + (size_t)L * h->ws_bytes + (size_t)L * 6 * sizeof(float) +
+                       (size_t)L * 4 * sizeof(double) + 4 * sizeof(int64_t) + 1024;
   cudaError_t e = cudaMalloc(&h->d_pool, total);
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_out, sizeof(float) * 4 * L);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking);
@@ -500,6 +501,8 @@ int mafed_host_step_create(const mafed_shape_t* shape, mafed_host_step_t** out) 
   for (int l = 0; l < L; ++l) { h->d_g.push_back(p); p += h->layer_bytes; }
   h->d_mask = reinterpret_cast<int64_t*>(p); p += h->mask_bytes;
   h->d_ws = p; p += (size_t)L * h->ws_bytes;
+  h->d_sums = reinterpret_cast<double*>(p); p += sizeof(double) * 4 * L;      // per layer [2 sums + 2 counts]
+  h->d_ticket = reinterpret_cast<int64_t*>(p); p += sizeof(int64_t) * 4;
   h->d_out = reinterpret_cast<float*>(p); p += sizeof(float) * 4 * L;
   h->d_scale = reinterpret_cast<float*>(p);
   h->ev_in.resize(L);
@@ -508,14 +511,16 @@ int mafed_host_step_create(const mafed_shape_t* shape, mafed_host_step_t** out) 
     cudaEventCreateWithFlags(&h->ev_in[l], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_run[l], cudaEventDisableTiming);
   }
+  cudaEventCreateWithFlags(&h->ev_mask, cudaEventDisableTiming);
   *out = h;
   return 0;
 }
 
 int mafed_host_step_run(mafed_host_step_t* h, const mafed_weights_t* weights, const void* const* h_student,
                         const void* const* h_teacher, void* const* h_grad, const int64_t* h_mask, float grad_out,
-                        float* h_out) {
+                        float* h_out, mafed_comm_t* comm) {
   if (!h || !weights || !h_student || !h_teacher || !h_grad || !h_out) return MAFED_E_ARG;
+  const bool sharded = comm != nullptr && comm->world > 1;
   const mafed_shape_t& sh = h->shape;
   const int L = sh.n_layers;
   if (needs_mask(sh) && !h_mask) return MAFED_E_ARG;
@@ -523,6 +528,15 @@ int mafed_host_step_run(mafed_host_step_t* h, const mafed_weights_t* weights, co
   const size_t mask = needs_mask(sh) ? (size_t)sh.B * (sh.T - sh.n_vis) * sizeof(int64_t) : 0;
   cudaError_t e = cudaSuccess;
   if (mask) e = cudaMemcpyAsync(h->d_mask, h_mask, mask, cudaMemcpyHostToDevice, h->s_in);
+  if (sharded && e == cudaSuccess) {
+    // batch-sharded: this rank's token counts leave for the peers as soon as the mask is on the device, while the
+    // first layer's activations are still crossing PCIe; every layer's step then reads the same ticket
+    e = cudaEventRecord(h->ev_mask, h->s_in);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->s_run, h->ev_mask, 0);
+    if (e != cudaSuccess) return (int)e;
+    int rc = mafed_distill_prefetch_counts(&sh, h->d_mask, comm, h->d_ticket, h->s_run);
+    if (rc) return rc;
+  }
   for (int l = 0; l < L && e == cudaSuccess; ++l) {
     e = cudaMemcpyAsync(h->d_s[l], h_student[l], layer, cudaMemcpyHostToDevice, h->s_in);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_t[l], h_teacher[l], layer, cudaMemcpyHostToDevice, h->s_in);
@@ -544,7 +558,8 @@ int mafed_host_step_run(mafed_host_step_t* h, const mafed_weights_t* weights, co
     void* gp[1] = {h->d_g[l]};
     char* ws = h->d_ws + (size_t)l * h->ws_bytes;
     int rc = mafed_distill_step(&one, sp, tp, gp, h->d_mask, &w, grad_out, ws, h->d_out + 4 * l, h->d_scale + 2 * l,
-                                nullptr, nullptr, nullptr, nullptr, nullptr, h->s_run);
+                                sharded ? h->d_sums + 4 * l : nullptr, nullptr, nullptr, sharded ? comm : nullptr,
+                                sharded ? h->d_ticket : nullptr, h->s_run);
     if (rc) return rc;
     cudaEventRecord(h->ev_run[l], h->s_run);
     cudaStreamWaitEvent(h->s_out, h->ev_run[l], 0);
@@ -570,6 +585,7 @@ int mafed_host_step_destroy(mafed_host_step_t* h) {
   if (!h) return 0;
   for (cudaEvent_t ev : h->ev_in) cudaEventDestroy(ev);
   for (cudaEvent_t ev : h->ev_run) cudaEventDestroy(ev);
+  if (h->ev_mask) cudaEventDestroy(h->ev_mask);
   if (h->s_in) cudaStreamDestroy(h->s_in);
   if (h->s_run) cudaStreamDestroy(h->s_run);
   if (h->s_out) cudaStreamDestroy(h->s_out);

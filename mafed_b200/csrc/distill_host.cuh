@@ -19,6 +19,9 @@ struct mafed_host_step {
   size_t ws_bytes = 0;
   float* d_out = nullptr;        // [L][4]
   float* d_scale = nullptr;      // [L][2]
+  double* d_sums = nullptr;      // [L][4] per-layer sums vector of a batch-sharded step
+  int64_t* d_ticket = nullptr;   // [4] token counts sent ahead of the step (batch-sharded)
+  cudaEvent_t ev_mask = nullptr;
   float* h_out = nullptr;        // pinned [L][4]
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_run;

@@ -9,6 +9,8 @@
 // binding loads) and fails loudly when that library is missing.
 #include <torch/extension.h>
 
+#include <ATen/cuda/CUDAEvent.h>
+#include <c10/cuda/CUDACachingAllocator.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <dlfcn.h>
@@ -106,6 +108,26 @@ struct Plan {
   }
   float fixed() const { return (float)(assumed_grad_out * grad_multiplier); }
 };
+
+// Token counts sent ahead of the step (mafed_distill_prefetch_counts).  The 1-CTA launch runs on a side stream,
+// ordered behind whatever produced the mask, so it never sits between two kernels of the compute stream; the step
+// that consumes the ticket makes its stream wait for `done` (long since recorded) before it launches.
+struct CountsTicket {
+  at::Tensor tensor;          // int64[4] on the device: {exchange epoch, bits(n_text), bits(n_vis rows), 0}
+  at::Tensor mask;            // the mask the counts were taken from (kept alive until the ticket goes)
+  at::cuda::CUDAEvent done;   // recorded on the side stream behind the launch
+  void wait() {
+    const auto dev = tensor.device();
+    done.block(c10::cuda::getCurrentCUDAStream(dev.index()));
+  }
+};
+
+c10::cuda::CUDAStream side_stream(c10::DeviceIndex dev) {
+  static std::vector<c10::optional<c10::cuda::CUDAStream>> streams(64);
+  auto& s = streams.at((size_t)dev);
+  if (!s.has_value()) s = c10::cuda::getStreamFromPool(/*isHighPriority=*/true, dev);
+  return *s;
+}
 
 int dtype_code(at::ScalarType t) {
   switch (t) {
@@ -224,7 +246,7 @@ struct DistillBackward : public Node {
 std::tuple<at::Tensor, at::Tensor, c10::optional<at::Tensor>> distill(
     const std::shared_ptr<Plan>& plan, std::vector<at::Tensor> students, std::vector<at::Tensor> teachers,
     const c10::optional<at::Tensor>& attn_mask, const py::object& masks_out, int64_t comm,
-    const c10::optional<at::Tensor>& ticket, const c10::optional<at::Tensor>& seen, int64_t tuning_addr) {
+    const std::shared_ptr<CountsTicket>& ticket, const c10::optional<at::Tensor>& seen, int64_t tuning_addr) {
   const Api& a = api();
   const int L = plan->n_layers;
   TORCH_CHECK((int)students.size() == L && (int)teachers.size() == L, "students / teachers / plan length mismatch");
@@ -335,7 +357,10 @@ std::tuple<at::Tensor, at::Tensor, c10::optional<at::Tensor>> distill(
   }
   const int64_t* mask_ptr = mask.defined() ? mask.data_ptr<int64_t>() : nullptr;
   const int64_t* ticket_ptr = nullptr;
-  if (ticket.has_value() && ticket->defined()) ticket_ptr = ticket->data_ptr<int64_t>();
+  if (ticket != nullptr) {
+    ticket->wait();     // this stream behind the prefetch launch (a no-op wait: it finished a forward pass ago)
+    ticket_ptr = ticket->tensor.data_ptr<int64_t>();
+  }
 
   at::Tensor grad_buf;
   if (plan->single_pass && any_need) {
@@ -395,14 +420,15 @@ std::tuple<at::Tensor, at::Tensor, c10::optional<at::Tensor>> distill(
   return std::make_tuple(std::move(total), std::move(aux), std::move(masks));
 }
 
-// Token counts ahead of the step (mafed_distill_prefetch_counts): returns the int64[4] ticket.
-at::Tensor prefetch_counts(const at::Tensor& attn_mask, int64_t n_vis, int64_t comm, int64_t tuning_addr) {
+// Token counts ahead of the step (mafed_distill_prefetch_counts): launches on the side stream, returns the ticket.
+std::shared_ptr<CountsTicket> prefetch_counts(const at::Tensor& attn_mask, int64_t n_vis, int64_t comm, int64_t tuning_addr) {
   const Api& a = api();
   TORCH_CHECK(attn_mask.is_cuda() && attn_mask.scalar_type() == at::kLong && attn_mask.is_contiguous() && attn_mask.dim() == 2,
               "prefetch_counts: attention_mask must be a contiguous int64 [B, txt] CUDA tensor");
   const auto device = attn_mask.device();
   c10::cuda::CUDAGuard guard(device);
-  const cudaStream_t stream = c10::cuda::getCurrentCUDAStream(device.index()).stream();
+  const auto current = c10::cuda::getCurrentCUDAStream(device.index());
+  const auto side = side_stream(device.index());
   mafed_shape_t shape;
   std::memset(&shape, 0, sizeof(shape));
   shape.n_layers = 1;
@@ -412,10 +438,19 @@ at::Tensor prefetch_counts(const at::Tensor& attn_mask, int64_t n_vis, int64_t c
   shape.D = 1;
   shape.dtype = MAFED_F32;
   shape.tuning = reinterpret_cast<const mafed_tuning_t*>(tuning_addr);
-  at::Tensor ticket = at::empty({4}, at::TensorOptions().dtype(at::kLong).device(device));
+  auto ticket = std::make_shared<CountsTicket>();
+  ticket->tensor = at::empty({4}, at::TensorOptions().dtype(at::kLong).device(device));
+  ticket->mask = attn_mask;
+  // both allocations belong to the compute stream; tell the allocator that the side stream touches them too
+  c10::cuda::CUDACachingAllocator::recordStream(ticket->tensor.storage().data_ptr(), side);
+  c10::cuda::CUDACachingAllocator::recordStream(attn_mask.storage().data_ptr(), side);
+  at::cuda::CUDAEvent ready;
+  ready.record(current);        // behind the producer of the mask
+  ready.block(side);
   check_rc(a.prefetch_counts(&shape, attn_mask.data_ptr<int64_t>(), reinterpret_cast<mafed_comm_t*>(comm),
-                             ticket.data_ptr<int64_t>(), stream),
+                             ticket->tensor.data_ptr<int64_t>(), side.stream()),
            "mafed_distill_prefetch_counts");
+  ticket->done.record(side);
   return ticket;
 }
 
@@ -435,6 +470,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("single_pass", &Plan::single_pass)
       .def_readwrite("assumed_grad_out", &Plan::assumed_grad_out)
       .def_readwrite("grad_multiplier", &Plan::grad_multiplier);
+  py::class_<CountsTicket, std::shared_ptr<CountsTicket>>(m, "CountsTicket")
+      .def_readonly("tensor", &CountsTicket::tensor)
+      .def("wait", &CountsTicket::wait, "make the current stream wait for the prefetch launch")
+      .def("data_ptr", [](CountsTicket& t) { return (uint64_t)(uintptr_t)t.tensor.data_ptr(); });
   m.def("distill", &distill, py::arg("plan"), py::arg("students"), py::arg("teachers"), py::arg("attn_mask"),
         py::arg("masks_out"), py::arg("comm"), py::arg("ticket"), py::arg("seen"), py::arg("tuning"));
   m.def("prefetch_counts", &prefetch_counts, py::arg("attn_mask"), py::arg("n_vis"), py::arg("comm"), py::arg("tuning"));

@@ -302,6 +302,16 @@ def distill_backward(ln: _Launch, grads: Sequence[Optional[torch.Tensor]], bwd_s
                                          _stream_ptr(ln.device)), "mafed_distill_bwd")
 
 
+def _ticket_ptr(ticket):
+    """Device address of a counts ticket (``node.prefetch_counts``); the current stream is made to wait for the
+    side-stream launch that fills it."""
+    if ticket is None:
+        return None
+    if hasattr(ticket, "wait"):
+        ticket.wait()
+    return ticket.data_ptr()
+
+
 def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group=None, mask_out=None, ticket=None):
     """One-pass step: counts -> gradient scale, loss sums + gradients from one read of student and teacher,
     losses -- a single launch of the fused kernel (``mafed_distill_step``); ``mask_out = (lang, image)`` int64
@@ -327,7 +337,7 @@ def distill_fused(students, teachers, grads, attn_mask, plan: DistillPlan, group
                 ln.shape_ref, ln.s_ptrs, ln.t_ptrs, g_ptrs, ln.mask_ptr, w, fixed, ws.data_ptr(), out.data_ptr(),
                 bwd_scale.data_ptr(), sums.data_ptr() if sums is not None else None,
                 lang.data_ptr() if lang is not None else None, image.data_ptr() if image is not None else None,
-                peer.handle if peer is not None else None, ticket.data_ptr() if ticket is not None else None, stream),
+                peer.handle if peer is not None else None, _ticket_ptr(ticket), stream),
                 "mafed_distill_step")
             return out, bwd_scale, ln
         if mask_out is not None:

@@ -125,6 +125,11 @@ class CHostStep:
         self.d2h_bytes = nbytes(self.h_g) + 4 * (1 + 3 * L)
         self.note = "C ABI mafed_host_step_run: pinned host student/teacher/mask -> device, one-pass fused kernel " \
                     "per layer, gradients + losses -> pinned host; 3-stream layer pipeline inside the library"
+        # batch-sharded runs hand the library the same peer-memory communicator the device-resident step uses
+        peer = method._peer() if hasattr(method, "_peer") else None
+        self.comm = peer.handle if peer is not None else None
+        if peer is not None:
+            self.note += "; batch-sharded: counts sent ahead once per step, sums exchanged per layer inside the kernels"
 
     def step(self, grad_out: float = 1.0) -> torch.Tensor:
         import ctypes
@@ -133,7 +138,7 @@ class CHostStep:
         with torch.cuda.device(self.device):
             cabi.check(self.lib.mafed_host_step_run(self.handle, ctypes.byref(self.weights), self.s_ptrs, self.t_ptrs,
                                                     self.g_ptrs, self.h_mask.data_ptr(), float(grad_out),
-                                                    self.h_out.data_ptr()), "mafed_host_step_run")
+                                                    self.h_out.data_ptr(), self.comm), "mafed_host_step_run")
         return self.h_out[0]
 
     def close(self):

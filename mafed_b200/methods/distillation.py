@@ -128,7 +128,7 @@ class FeatureDistillation(CLStrategy):
         self.last_layer_losses: Optional[torch.Tensor] = None   # device [3L]: layer, then (text, vision)
         self.last_layers: List[int] = []
         self._pending_logs = deque()
-        self._ticket = None                                  # (attention_mask, its version, ticket) of prefetch_counts
+        self._tickets = {}                                   # id(attention_mask) -> (mask, its version, ticket)
 
     # ------------------------------------------------------------------ trainer hooks
     def update(self, dataset, model, dataloader, mask=None, **kwargs):
@@ -206,8 +206,10 @@ class FeatureDistillation(CLStrategy):
         """Send this rank's token counts to the peers ahead of the step (batch-sharded runs).  The counts depend
         only on ``attention_mask``, which is known as soon as the memory batch is drawn -- before the student
         forward (``distillation.py:85-91``) -- so the step's kernel later finds the global counts in its own
-        mailbox instead of exchanging them at its start.  ``replay`` calls this itself; a trainer that draws batches
-        ahead may call it up to two steps early.  No-op on a single rank unless ``force``."""
+        mailbox instead of exchanging them at its start.  The 1-CTA launch goes to a side stream (ordered behind the
+        producer of the mask), so it does not sit between kernels of the compute stream.  ``replay`` calls this itself;
+        a trainer that draws batches ahead may call it up to two steps early (every rank alike: the call is part of
+        the exchange sequence).  No-op on a single rank unless ``force``."""
         attn = batch.get("attention_mask") if hasattr(batch, "get") else None
         if attn is None or not attn.is_cuda or attn.dtype != torch.int64 or not attn.is_contiguous():
             return None
@@ -217,7 +219,9 @@ class FeatureDistillation(CLStrategy):
         from mafed_b200 import node
         ticket = node.load().prefetch_counts(attn, self.num_vision_tokens, peer.handle.value if peer is not None else 0,
                                              cabi.active_tuning_address())
-        self._ticket = (attn, attn._version, ticket)
+        if len(self._tickets) >= 3:          # at most 3 batches ahead (the mailbox keeps 4 generations of counts)
+            self._tickets.pop(next(iter(self._tickets)))
+        self._tickets[id(attn)] = (attn, attn._version, ticket)
         return ticket
 
     def _peer(self):
@@ -318,10 +322,9 @@ class FeatureDistillation(CLStrategy):
                     mask_out = True
                 else:
                     batch["lang_masks"], batch["image_masks"] = modality_masks(attn, self.num_vision_tokens)
-            tk = self._ticket
-            if tk is not None:
-                self._ticket = None
-                if tk[0] is attn and tk[1] == attn._version:
+            if self._tickets:
+                tk = self._tickets.pop(id(attn), None)
+                if tk is not None and tk[0] is attn and tk[1] == attn._version:
                     ticket = tk[2]
         if plan.single_pass and self._gout_seen is None:
             self._gout_seen = seen_slot()

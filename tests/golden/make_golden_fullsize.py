@@ -1,10 +1,11 @@
 """Golden outputs of the UNMODIFIED reference at BASELINE.json's configurations -- full size.
 
-    python tests/golden/make_golden_fullsize.py [C1 C2 C4]      (build container only: needs /root/reference)
+    python tests/golden/make_golden_fullsize.py [C1 C2 C3 C4 C2cos]      (build container only: needs /root/reference)
 
 C1 = configs[0] "VLPythia-base (12 layers, d=768) ... batch 8, 256 visual + 32 text tokens, fp32, on CPU";
-C2 = configs[1] the same model at batch 128 in bf16; C4 = configs[3]'s per-GPU shard, VLPythia-1B (16 layers,
-d=2048), 64 samples, bf16.  Everywhere the reference's own call num_hidden_layers = L - 1 (train.py:133) and the
+C2 = configs[1] the same model at batch 128 in bf16; C3 = configs[2] VLPythia-410M (24 layers, d=1024), batch 256,
+bf16; C4 = configs[3]'s per-GPU shard, VLPythia-1B (16 layers, d=2048), 64 samples, bf16; C2cos = the C2 shape with
+the cosine token loss and the count-weighted ("equal") modality strategy.  Everywhere the reference's own call num_hidden_layers = L - 1 (train.py:133) and the
 shipped recipe mse / balanced / discounted gamma 0.5 (scripts/run_seed42.sh:74-93); bf16 runs under
 torch.autocast(bfloat16) as distillation.py:90 does (CPU autocast here).
 The inputs (up to 2 x 1.1 GB) are not committed: they are regenerated from the seed with oracle.make_inputs (torch
@@ -30,6 +31,11 @@ CONFIGS = {
     "C1": dict(BASE, num_hidden_layers=11, n_tuple=13, bsz=8, dim=768, dtype="fp32"),
     "C2": dict(BASE, num_hidden_layers=11, n_tuple=13, bsz=128, dim=768, dtype="bf16"),
     "C4": dict(BASE, num_hidden_layers=15, n_tuple=17, bsz=64, dim=2048, dtype="bf16"),
+    # configs[2]: VLPythia-410M (24 layers, d=1024), batch 256, bf16 (the +ER part is the LM loss, outside the path)
+    "C3": dict(BASE, num_hidden_layers=23, n_tuple=25, bsz=256, dim=1024, dtype="bf16", tags=("ragged",)),
+    # the other loss / modality strategy at full size: cosine token loss, count-weighted ("equal") modalities
+    "C2cos": dict(BASE, num_hidden_layers=11, n_tuple=13, bsz=128, dim=768, dtype="bf16", loss="cosine", modality="equal",
+                  tags=("ragged",)),
 }
 SEED = 1234
 N_SAMPLES = 256
@@ -47,7 +53,7 @@ def main():
         case = CONFIGS[name]
         dtype = torch.bfloat16 if case["dtype"] == "bf16" else torch.float32
         blob = {}
-        for tag in ("ragged", "ones"):
+        for tag in case.get("tags", ("ragged", "ones")):
             st, te, am = make_inputs(case["n_tuple"], case["bsz"], case["txt"], case["dim"], n_vis=case["n_vis"],
                                      dtype=dtype, seed=SEED, teacher=case["teacher"], mask=tag)
             loss, logged, grads = run_reference(case, st, te, am)

@@ -1,7 +1,8 @@
 """BASELINE.json's configurations at FULL size against outputs of the unmodified reference
-(tests/golden/fullsize_{C1,C2,C4}.npz, made by tests/golden/make_golden_fullsize.py): the oracle on the CPU at C1
-(not gpu) and the CUDA path through the mirrored API at C1 (configs[0], fp32), C2 (configs[1], bf16) and the C4
-per-GPU shard (configs[3], bf16) (gpu).  Inputs are regenerated from the seed; their digests are checked first."""
+(tests/golden/fullsize_{C1,C2,C3,C4,C2cos}.npz, made by tests/golden/make_golden_fullsize.py): the oracle on the CPU
+at C1 (not gpu) and the CUDA path through the mirrored API at C1 (configs[0], fp32), C2 (configs[1], bf16), C3
+(configs[2], VLPythia-410M, batch 256, bf16), the C4 per-GPU shard (configs[3], bf16) and C2 with the cosine loss
+and count-weighted modalities (gpu).  Inputs are regenerated from the seed; their digests are checked first."""
 import os
 
 import numpy as np
@@ -17,7 +18,11 @@ CONFIGS = {
     "C1": dict(BASE, num_hidden_layers=11, n_tuple=13, bsz=8, dim=768, dtype=torch.float32),
     "C2": dict(BASE, num_hidden_layers=11, n_tuple=13, bsz=128, dim=768, dtype=torch.bfloat16),
     "C4": dict(BASE, num_hidden_layers=15, n_tuple=17, bsz=64, dim=2048, dtype=torch.bfloat16),
+    "C3": dict(BASE, num_hidden_layers=23, n_tuple=25, bsz=256, dim=1024, dtype=torch.bfloat16),
+    "C2cos": dict(BASE, num_hidden_layers=11, n_tuple=13, bsz=128, dim=768, dtype=torch.bfloat16, loss="cosine",
+                  modality="equal"),
 }
+TAGS = {"C3": ("ragged",), "C2cos": ("ragged",)}     # configurations generated with one mask variant only
 
 
 def _tol(case):
@@ -69,7 +74,7 @@ def _check(case, z, tag, loss, layer_losses, grads):
     assert all(grads[l] is None for l in range(nh, case["n_tuple"]))   # the reference leaves the tail untouched
 
 
-@pytest.mark.parametrize("name,tag", [("C1", "ragged"), ("C1", "ones"), ("C2", "ragged")])
+@pytest.mark.parametrize("name,tag", [("C1", "ragged"), ("C1", "ones"), ("C2", "ragged"), ("C2cos", "ragged")])
 def test_oracle_matches_reference_at_full_size(name, tag):
     """The CPU restatement against the unmodified reference at configs[0] (fp32) and configs[1] (bf16 autocast)."""
     from golden_util import oracle_cfg
@@ -85,6 +90,8 @@ def test_oracle_matches_reference_at_full_size(name, tag):
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_cuda_path_matches_reference_at_full_size(name, tag, single_pass):
     from gpu_util import run_product
+    if tag not in TAGS.get(name, ("ragged", "ones")):
+        pytest.skip("this configuration's golden holds the ragged mask only")
     case, z = CONFIGS[name], _golden(name)
     st, te, am = _inputs(case, z, tag)
     out = run_product(dict(case), st, te, am, single_pass=single_pass)

@@ -10,8 +10,12 @@ class _Out:
 
 
 class TinyVL(nn.Module):
-    def __init__(self, n_vis=8, dim=64, layers=3, vocab=97, patch=12):
+    def __init__(self, n_vis=8, dim=64, layers=3, vocab=97, patch=12, fp32_island=False):
+        """``fp32_island``: run the whole forward with autocast disabled, so that the model computes the same fp32
+        numbers on the CPU (where the reference's ``torch.autocast("cuda", ...)`` region is inert) and on the GPU
+        -- what the reference-generated replay goldens need."""
         super().__init__()
+        self.fp32_island = fp32_island
         from transformers import GPTNeoXConfig, GPTNeoXModel
         cfg = GPTNeoXConfig(hidden_size=dim, num_hidden_layers=layers, num_attention_heads=4, intermediate_size=2 * dim,
                             vocab_size=vocab, max_position_embeddings=128, hidden_dropout=0.0, attention_dropout=0.0)
@@ -22,6 +26,12 @@ class TinyVL(nn.Module):
 
     def forward(self, input_ids=None, pixel_values=None, attention_mask=None, labels=None, compute_loss=False,
                 output_hidden_states=False, allow_input_gradients=False, return_dict=True, **kwargs):
+        if self.fp32_island and torch.is_autocast_enabled(pixel_values.device.type):
+            with torch.autocast(pixel_values.device.type, enabled=False):
+                return self._forward(input_ids, pixel_values, attention_mask, labels, output_hidden_states)
+        return self._forward(input_ids, pixel_values, attention_mask, labels, output_hidden_states)
+
+    def _forward(self, input_ids, pixel_values, attention_mask, labels, output_hidden_states):
         vision = self.connector(pixel_values)                         # [B, n_vis, D]
         text = self.gpt_neox.embed_in(input_ids)                      # [B, txt, D]
         embeds = torch.cat([vision, text], dim=1)
