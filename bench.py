@@ -628,7 +628,7 @@ def other_workloads(ctx, skip, steps=100, warmup=20):
     for name, (desc, n_tuple, n_sel, B, txt, D, dt), loss in rows:
         if name == skip:
             continue
-        rec = measure_point(ctx, n_sel, B, txt, D, dt, False, steps, warmup, loss=loss, kernel_level=False,
+        rec = measure_point(ctx, n_sel, B, txt, D, dt, False, steps, warmup, loss=loss, kernel_level=True,
                             graphed=name in ("C1", "C2"))
         esize = 4 if dt == "fp32" else 2
         rec.update({"workload": desc + (f" [{loss}]" if loss != "mse" else "") + (" [fp32 hidden states]" if name.endswith("fp32") else ""),
@@ -827,6 +827,30 @@ def run_main(ctx):
     fwd_ms, bwd_ms, two_raw_ms = stage_loop(two_pass_step)
     fused_ms, gate_ms, one_raw_ms = stage_loop(one_pass_step)
 
+    # what the backward's check of the upstream gradient costs a step: back-to-back kernel-level steps (no events
+    # inside the loop) with no check at all, with the 1-CTA gate, and with round 1's form (the whole persistent
+    # backward grid launched to read one float and return)
+    def plain_loop(mode):
+        from mafed_b200 import cabi
+        def one(i):
+            out, scale, ln = distill_fused(st, te, grads, masks[i % 2], plan, group=False)
+            if mode:
+                distill_backward(ln, grads, scale, gout, skip_if_equals=fixed, grad_out_scale=plan.grad_multiplier)
+        with cabi.tuning(TUNE_NO_GATE=1) if mode == "full_grid" else _Null():
+            for i in range(args.warmup):
+                one(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.steps):
+                one(i)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+    base_ms = min(plain_loop(None) for _ in range(2))
+    gate_loop_ms = min(plain_loop("gate") for _ in range(2))
+    full_loop_ms = min(plain_loop("full_grid") for _ in range(2))
+
     # ---- (2) the public API: the headline `value`
     fd.single_pass = False
     two_api_ms, _, _ = loop.timed(args.steps, args.warmup)
@@ -875,7 +899,14 @@ def run_main(ctx):
                      "achieved": gbs(fused_bytes, fused_ms), "peak": peak, "unit": "GB/s",
                      "frac": gbs(fused_bytes, fused_ms) / peak, "traffic": measured_traffic(wl), "peak_source": peak_src,
                      "bytes_per_launch": fused_bytes, "bytes_per_unit": 3 * row_bytes, "ms_per_launch": fused_ms,
-                     "gate_launch_ms": gate_ms, "fixup_launch_ms": gate_ms},
+                     "gate_launch_ms": max(0.0, gate_loop_ms - base_ms), "fixup_launch_ms": max(0.0, gate_loop_ms - base_ms),
+                     "gate": {"what": "per-step cost of checking the upstream gradient in backward, from back-to-back "
+                                      "kernel-level steps on this rank: fused kernel alone / + 1-CTA gate (the product) "
+                                      "/ + the full persistent grid that returns at once (round 1)",
+                              "fused_only_ms_per_step": base_ms, "with_gate_ms_per_step": gate_loop_ms,
+                              "with_full_grid_fixup_ms_per_step": full_loop_ms,
+                              "gate_us": (gate_loop_ms - base_ms) * 1e3, "full_grid_us": (full_loop_ms - base_ms) * 1e3,
+                              "gate_event_pair_ms": gate_ms}},
         "roofline_step": {"achieved": gbs(fused_bytes, ms_per_step), "peak": peak, "unit": "GB/s",
                           "frac": gbs(fused_bytes, ms_per_step) / peak,
                           "frac_of_nominal_8000": gbs(fused_bytes, ms_per_step) / 8000.0, "bytes_per_unit": 3 * row_bytes},
@@ -924,6 +955,7 @@ def run_main(ctx):
                                   "the slowest GPU every step: ms_per_step vs max(uncoupled) is the cost of the exchange "
                                   "itself, max(uncoupled) vs the 1-GPU run is GPU-to-GPU variation")
     line["clocks"] = sampler.summary()
+    line["api_minus_kernel_loop_us"] = (ms_per_step - gate_loop_ms) * 1e3 if world == 1 else None
 
     if not args.no_c5:
         try:

@@ -122,6 +122,10 @@ template <> struct Pack<float> {
   }
   __device__ __forceinline__ static float load1(const void* p, long long i) { return ((const float*)p)[i]; }
   __device__ __forceinline__ static void store1(void* p, long long i, float v) { ((float*)p)[i] = v; }
+  // one 32-bit word at a time (keeps few values live: the register-resident row forms)
+  static constexpr int kPerWord = 1;
+  __device__ __forceinline__ static void unpack_word(uint32_t w, float (&f)[1]) { f[0] = __uint_as_float(w); }
+  __device__ __forceinline__ static uint32_t pack_word(const float (&f)[1]) { return __float_as_uint(f[0]); }
 };
 
 template <> struct Pack<__nv_bfloat16> {
@@ -140,6 +144,12 @@ template <> struct Pack<__nv_bfloat16> {
   __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
     return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
   }
+  static constexpr int kPerWord = 2;
+  __device__ __forceinline__ static void unpack_word(uint32_t w, float (&f)[2]) {
+    f[0] = __uint_as_float(w << 16);
+    f[1] = __uint_as_float(w & 0xffff0000u);
+  }
+  __device__ __forceinline__ static uint32_t pack_word(const float (&f)[2]) { return pack2(f[0], f[1]); }
   __device__ __forceinline__ static float load1(const void* p, long long i) {
     return __bfloat162float(((const __nv_bfloat16*)p)[i]);
   }
@@ -164,6 +174,9 @@ template <> struct Pack<__half> {
   __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
     return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
   }
+  static constexpr int kPerWord = 2;
+  __device__ __forceinline__ static void unpack_word(uint32_t w, float (&f)[2]) { up2(w, f[0], f[1]); }
+  __device__ __forceinline__ static uint32_t pack_word(const float (&f)[2]) { return pack2(f[0], f[1]); }
   __device__ __forceinline__ static float load1(const void* p, long long i) {
     return __half2float(((const __half*)p)[i]);
   }

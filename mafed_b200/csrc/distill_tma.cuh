@@ -291,6 +291,84 @@ __device__ __forceinline__ void grad_elems_tma(const float (&a)[NE], const float
   }
 }
 
+// Cosine gradient of one SHORT row of exactly 32 * CPL chunks with compile-time trip counts: the shared-memory loads
+// of a batch are issued back to back, there is no loop control, and the row scalars cost one reciprocal instead of
+// three divisions.  KEEP: the lane's share of the row pair stays in registers between the statistics and the gradient
+// (no second sweep over shared memory) -- affordable up to CPL = 3 in the 16-warp build (96 registers per thread);
+// otherwise the row is swept twice in batches of two chunks.  At 1.5-2 KB rows the generic two-sweep loop further
+// down is bound by instruction issue (61 % of the issue slots at 4 warps per scheduler,
+// profiles/r02a_ncu_fused_C2_cosine_raw.csv), not by HBM.  Returns the row's loss value 1 - cos (all lanes hold it).
+template <typename T>
+__device__ __forceinline__ void cosine_stats_chunk(const uint4& sv, const uint4& tv, float& x, float& y, float& z) {
+  constexpr int NW = Pack<T>::kPerWord;
+  // word by word, so that only a handful of unpacked values is live at any time
+  const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float a[NW], b[NW];
+    Pack<T>::unpack_word(sw[k], a);
+    Pack<T>::unpack_word(tw[k], b);
+    accumulate<MAFED_LOSS_COSINE, NW>(a, b, x, y, z);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 cosine_grad_chunk(const uint4& sv, const uint4& tv, float ch, float cp) {
+  constexpr int NW = Pack<T>::kPerWord;
+  const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w}, tw[4] = {tv.x, tv.y, tv.z, tv.w};
+  uint32_t ow[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float a[NW], b[NW], o[NW];
+    Pack<T>::unpack_word(sw[k], a);
+    Pack<T>::unpack_word(tw[k], b);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) o[i] = fmaf(ch, a[i], -cp * b[i]);
+    ow[k] = Pack<T>::pack_word(o);
+  }
+  return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+template <typename T, int CPL, bool KEEP>
+__device__ __forceinline__ float cosine_row_unrolled(uint32_t sa, uint32_t ta, int lane, float w, char* grow) {
+  constexpr int NB = KEEP ? CPL : 2;          // chunks per batch of loads
+  static_assert(CPL % NB == 0, "batches of two chunks");
+  uint4 sv[NB], tv[NB];
+  float x = 0.f, y = 0.f, z = 0.f;
+#pragma unroll
+  for (int u0 = 0; u0 < CPL; u0 += NB) {
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      sv[u] = lds_128(sa + (uint32_t)(lane + 32 * (u0 + u)) * 16u);
+      tv[u] = lds_128(ta + (uint32_t)(lane + 32 * (u0 + u)) * 16u);
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) cosine_stats_chunk<T>(sv[u], tv[u], x, y, z);
+  }
+  x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
+  // cos = x / den, den = sqrt((|h|^2 + eps)(|p|^2 + eps));  d(1 - cos)/dh = (cos / (|h|^2 + eps)) h - p / den
+  const float aa = y + kCosEps, den = sqrtf(aa * (z + kCosEps));
+  const float r = __frcp_rn(den * aa);          // one correctly rounded reciprocal serves both quotients
+  const float inv_den = r * aa, cosv = x * inv_den;
+  const float ch = w * cosv * (r * den), cp = w * inv_den;
+  if (grow != nullptr) {
+#pragma unroll
+    for (int u0 = 0; u0 < CPL; u0 += NB) {
+      if (!KEEP) {
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+          sv[u] = lds_128(sa + (uint32_t)(lane + 32 * (u0 + u)) * 16u);
+          tv[u] = lds_128(ta + (uint32_t)(lane + 32 * (u0 + u)) * 16u);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NB; ++u)
+        stg_128(grow + (lane + 32 * (u0 + u)) * 16, cosine_grad_chunk<T>(sv[u], tv[u], ch, cp));
+    }
+  }
+  return 1.f - cosv;
+}
+
 // MODE = kBackward: gradients only.  MODE = kFused: the consumers also accumulate the forward's loss
 // sums from the rows they already hold in shared memory (one pass over student and teacher per step).
 template <typename T, int LOSS, int NCW, int MODE>
@@ -460,6 +538,18 @@ k_bwd_tma(const __grid_constant__ PathParams p, const __grid_constant__ TmaGeom 
         }
         const uint32_t sa = s_base + (uint32_t)r * row_bytes, ta = t_base + (uint32_t)r * row_bytes;
         float ch = 0.f, cp = 0.f, rowval = 0.f;
+        if (LOSS == MAFED_LOSS_COSINE && NCW == 16 && (p.n_chunks == 96 || p.n_chunks == 128 || p.n_chunks == 192)) {
+          // short rows (1.5 / 2 / 3 KB: base and 410M hidden sizes in bf16, base in fp32): fully unrolled forms
+          float val;
+          if (p.n_chunks == 96) val = cosine_row_unrolled<T, 3, true>(sa, ta, lane, w, gb != nullptr ? grow : nullptr);
+          else if (p.n_chunks == 128) val = cosine_row_unrolled<T, 4, false>(sa, ta, lane, w, gb != nullptr ? grow : nullptr);
+          else val = cosine_row_unrolled<T, 6, false>(sa, ta, lane, w, gb != nullptr ? grow : nullptr);
+          if (FUSED && lane == 0) {
+            if (mt.mod[r] == 0) acc_text = fmaf(mt.w[r], val, acc_text);
+            else acc_vis = fmaf(mt.w[r], val, acc_vis);
+          }
+          continue;
+        }
         if (LOSS == MAFED_LOSS_COSINE && NCW == 8 && p.n_chunks <= 256) {
           // cosine, rows up to 4 KB, 8-warp build only (the 16-warp default has no register room for it and
           // hides the latency of the two-pass form better, profiles/): the lane's share of the row pair lives in
