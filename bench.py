@@ -855,12 +855,8 @@ def run_main(ctx):
     fd.single_pass = False
     two_api_ms, _, _ = loop.timed(args.steps, args.warmup)
     fd.single_pass = True
-    trace0 = peer.trace() if peer is not None else None
-    sampler = ClockSampler(ctx.local_rank)
-    api_ms, host_us, loss = loop.timed(args.steps, args.warmup, sampler)
-    trace1 = peer.trace() if peer is not None else None
-    uncoupled = None
-    if world > 1:
+
+    def uncoupled_loop():
         # the same API step with the exchange switched off (per-rank loss), all ranks at once: what every GPU does on
         # its own.  The coupled step cannot be faster than the slowest of these.
         fd.process_group = False
@@ -869,7 +865,18 @@ def run_main(ctx):
         own = torch.tensor([own_ms / args.steps], dtype=torch.float64, device=device)
         every = [torch.zeros_like(own) for _ in range(world)]
         dist.all_gather(every, own)
-        uncoupled = [float(x) for x in every]
+        return [float(x) for x in every]
+
+    # (the uncoupled loop runs before AND after the coupled one: step times drift by ~1 % as the GPUs warm up)
+    uncoupled_before = uncoupled_loop() if world > 1 else None
+    trace0 = peer.trace() if peer is not None else None
+    sampler = ClockSampler(ctx.local_rank)
+    api_ms, host_us, loss = loop.timed(args.steps, args.warmup, sampler)
+    trace1 = peer.trace() if peer is not None else None
+    uncoupled = None
+    if world > 1:
+        uncoupled_after = uncoupled_loop()
+        uncoupled = [0.5 * (a + b) for a, b in zip(uncoupled_before, uncoupled_after)]
     api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms = ctx.max_over_ranks(
         [api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms])
     ms_per_step = api_ms / args.steps
@@ -950,6 +957,7 @@ def run_main(ctx):
             "steps_traced": calls, "includes_warmup": True}
     if uncoupled is not None:
         line["uncoupled_ms_per_rank"] = uncoupled
+        line["uncoupled_ms_per_rank_before_after"] = [uncoupled_before, uncoupled_after]
         line["coupling_cost_us"] = (ms_per_step - max(uncoupled)) * 1e3
         line["uncoupled_note"] = ("API step with the exchange off, all ranks running at once; the coupled step waits for "
                                   "the slowest GPU every step: ms_per_step vs max(uncoupled) is the cost of the exchange "

@@ -44,6 +44,31 @@ def _worker(rank, world, port, ret):
                          distillation_layer=None, num_vision_tokens=8)
     ref = O.forward_backward(st, te, am, cfg)
     assert abs(loss - float(ref["loss"])) / float(ref["loss"]) < 1e-5
+    # with a process group the strategy returns the GLOBAL-batch loss, and DDP will average the
+    # parameter gradients over the ranks -- so by default the step multiplies its gradients by world_size; an explicit
+    # grad_multiplier (gradients summed, not averaged) or process_group=False (per-rank loss) turns that off
+    from mafed_b200.methods import CLMethod
+
+    class Opts:
+        tasks = ["a", "b", "c"]; batch_size = 4; seed = 42; pin_mem = False; accumulate_grad_batches = 4
+
+    def make(**kw):
+        return CLMethod["featdistill"](memory_size=8, opts=Opts(), model_type="vlpythia",
+                                       distillation_modality_weighing_strategy="balanced",
+                                       distillation_layer_weighing_strategy="equal", distillation_layer=None,
+                                       num_hidden_layers=3, **kw)
+
+    def multiplier(fd):
+        coeffs, kind, lang = fd._tables([0, 1, 2])
+        return fd._plan([0, 1, 2], coeffs, 1.0, kind, lang).grad_multiplier
+
+    assert multiplier(make()) == float(world)
+    assert multiplier(make(grad_multiplier=1.0)) == 1.0
+    assert multiplier(make(process_group=False)) == 1.0
+    fd = make()
+    assert fd.assumed_grad_out == 0.25                      # 1 / accumulate_grad_batches
+    plan = fd._step_plan([0, 1, 2])
+    assert plan.grad_multiplier == float(world) and plan.assumed_grad_out == 0.25
     ret[rank] = True
     dist.destroy_process_group()
 

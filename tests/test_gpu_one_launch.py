@@ -233,5 +233,21 @@ def test_missing_peer_poisons_the_step_instead_of_hanging():
         status = ctypes.c_int(0)
         assert lib.mafed_comm_status(handle, ctypes.byref(status)) == 0 and status.value == 1
         assert torch.isnan(out[0]) and all(torch.isnan(x).any() for x in g)
+        # the strategy notices by itself: the status word is mapped host memory, read (no sync) by every distill()
+        from gpu_util import make_method
+        from mafed_b200 import comm as C
+        key = (0, torch.cuda.current_device())
+        saved = C._cache.get(key, "absent")
+        C._cache[key] = C.PeerComm(handle, 2, 0)
+        try:
+            fd = make_method(dict(modality="equal", layer_strategy="discounted", loss="mse", gamma=0.5,
+                                  num_hidden_layers=L, layer=None, n_vis=256, coeff=1.0, cls=False, lang_coeff=None))
+            with pytest.raises(cabi.MafedDistillError, match="did not reach a distillation exchange"):
+                fd.check_exchange(sync=False)
+        finally:
+            if saved == "absent":
+                C._cache.pop(key, None)
+            else:
+                C._cache[key] = saved
     finally:
         lib.mafed_comm_destroy(handle)

@@ -210,3 +210,40 @@ def test_strategy_state_roundtrip():
     bare.load_state_dict(state)
     bare._update_memory(_ToyDataset(50))
     assert len(bare.datasets) == 1
+
+
+def test_assumed_upstream_gradient_follows_the_gate(monkeypatch):
+    """The backward gate leaves the upstream gradient it saw in a pinned word; the next distill() re-aims
+    `assumed_grad_out` at it (host logic only: the word is faked here)."""
+    import numpy as np
+    fd = FeatureDistillation(8, Opts(), "vlpythia", distillation_modality_weighing_strategy="balanced",
+                             distillation_layer_weighing_strategy="equal", distillation_layer=None, num_hidden_layers=2)
+    assert fd.assumed_grad_out == 1.0 / Opts.accumulate_grad_batches and fd.adapt_assumed_grad_out and fd.single_pass
+    fd.assumed_grad_out = 1.0
+    word = np.zeros(1, dtype=np.float32)
+    fd._gout_seen_np = word
+    fd._adapt_assumed()
+    assert fd.assumed_grad_out == 1.0                       # nothing seen yet (0 = no backward has run)
+    for bad in (float("nan"), float("inf")):
+        word[0] = bad
+        fd._adapt_assumed()
+        assert fd.assumed_grad_out == 1.0                   # an overflowed / poisoned step teaches nothing
+    word[0] = 0.25
+    fd._adapt_assumed()
+    assert fd.assumed_grad_out == 0.25 and fd._gout_changes == 1
+    fd._adapt_assumed()
+    assert fd._gout_changes == 1                            # unchanged value: no churn
+    plan = fd._step_plan([0, 1])
+    assert plan.assumed_grad_out == 0.25                    # the plan cache follows
+    # under a gradient multiplier the gate sees grad_out * multiplier
+    fd.grad_multiplier = 4.0
+    plan = fd._step_plan([0, 1])
+    assert plan.grad_multiplier == 4.0
+    word[0] = 2.0
+    fd._adapt_assumed()
+    assert fd.assumed_grad_out == 0.5
+    # an upstream gradient that never settles (dynamic loss scaling) -> two-pass form
+    for i in range(12):
+        word[0] = float(2 ** (i + 2))
+        fd._adapt_assumed()
+    assert not fd.single_pass
