@@ -231,10 +231,14 @@ int launch_ldg(const mafed_shape_t& sh, const PathParams& p, const Launcher& go)
 template <typename T, int LOSS, int PASS, typename Launcher>
 int dispatch_ldg(const mafed_shape_t& sh, const PathParams& p, const Launcher& go) {
   const int cpl = (p.n_chunks + 31) / 32;
-  if (cpl <= 1) return launch_ldg<T, 1, 4, LOSS, PASS>(sh, p, go);
-  if (cpl <= 2) return launch_ldg<T, 2, 4, LOSS, PASS>(sh, p, go);
-  if (cpl <= 3) return launch_ldg<T, 3, 2, LOSS, PASS>(sh, p, go);
-  if (cpl <= 4) return launch_ldg<T, 4, 2, LOSS, PASS>(sh, p, go);
+  // rows per warp per iteration: more independent loads in flight for short rows; the cosine gradient keeps the row
+  // statistics and two coefficients per row as well, so it takes half as many rows at a time (with 4 / 2 it spilled
+  // 150-250 bytes per thread under the 128-register cap)
+  constexpr bool kHeavy = LOSS == MAFED_LOSS_COSINE && PASS != kPassFwd;
+  if (cpl <= 1) return launch_ldg<T, 1, kHeavy ? 2 : 4, LOSS, PASS>(sh, p, go);
+  if (cpl <= 2) return launch_ldg<T, 2, kHeavy ? 2 : 4, LOSS, PASS>(sh, p, go);
+  if (cpl <= 3) return launch_ldg<T, 3, kHeavy ? 1 : 2, LOSS, PASS>(sh, p, go);
+  if (cpl <= 4) return launch_ldg<T, 4, kHeavy ? 1 : 2, LOSS, PASS>(sh, p, go);
   if (cpl <= 6) return launch_ldg<T, 6, 1, LOSS, PASS>(sh, p, go);
   return launch_ldg<T, 8, 1, LOSS, PASS>(sh, p, go);  // multi-pass for rows longer than 4 KB
 }

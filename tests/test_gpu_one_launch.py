@@ -251,3 +251,48 @@ def test_missing_peer_poisons_the_step_instead_of_hanging():
                 C._cache[key] = saved
     finally:
         lib.mafed_comm_destroy(handle)
+
+
+@pytest.mark.parametrize("B,txt", [(5, 9), (70, 256)], ids=["small-mask", "mask-over-16Ki"])
+def test_counts_prefetched_on_one_rank(B, txt):
+    """`prefetch_counts(force=True)` on a single rank: the step reads the token counts from the ticket instead of
+    summing the mask itself -- which also keeps a step with a large mask (> 16 Ki entries) a single launch.  Same
+    bits as the step without a ticket; a ticket whose mask was edited afterwards is ignored."""
+    from gpu_util import Out, make_method
+    from golden_util import oracle_cfg
+    L, D = 2, 256
+    st, te, am = O.make_inputs(L + 1, B, txt, D, n_vis=256, dtype=torch.bfloat16, seed=17)
+    meta = dict(modality="equal", layer_strategy="discounted", loss="mse", gamma=0.5, num_hidden_layers=L, layer=None,
+                n_vis=256, coeff=1.0, cls=False, lang_coeff=None)
+    ref = O.forward_backward(st, te, am, oracle_cfg(meta))
+    te_c = [t.cuda() for t in te]
+
+    def run(prefetch, touch=False):
+        fd = make_method(meta)
+        fd.past_model = lambda **kw: Out(tuple(te_c))
+        leaves = [s.cuda().requires_grad_(True) for s in st]
+        mask = am.cuda()
+        batch = {"attention_mask": mask}
+        if prefetch:
+            ticket = fd.prefetch_counts(batch, force=True)
+            assert ticket is not None and len(fd._tickets) == 1
+            if touch:
+                mask.mul_(1)                                   # bumps the tensor's version: the ticket is stale
+        loss = fd.distill(Out(tuple(leaves)), batch)
+        assert not fd._tickets
+        loss.backward()
+        torch.cuda.synchronize()
+        if prefetch and not touch:
+            tk = ticket.tensor.cpu()
+            assert int(tk[0]) == 0                             # no exchange epoch on a single rank
+            assert tk[1:3].view(torch.float64).tolist() == [float(am.sum()), float(B * 256)]
+        return loss.detach(), [x.grad for x in leaves]
+
+    base_loss, base_grads = run(False)
+    for kwargs in (dict(prefetch=True), dict(prefetch=True, touch=True)):
+        loss, grads = run(**kwargs)
+        assert torch.equal(loss, base_loss)
+        assert all(torch.equal(a, b) for a, b in zip(grads[:L], base_grads[:L]))
+    assert float(base_loss) == pytest.approx(float(ref["loss"]), rel=2e-3)
+    for l in range(L):
+        assert rel_err(base_grads[l].float().cpu(), ref["grads"][l].float()) < 2e-3
