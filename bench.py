@@ -581,10 +581,12 @@ def measure_point(ctx, n_sel, B, txt, D, dt, ragged, steps, warmup, loss="mse", 
                                                         graph_ms if graph_ms is not None else 0.0])
     ms = api_ms / steps
     units = B * T * n_sel * world
-    live = live_rows(masks, N_VIS) * n_sel            # rows streamed on THIS rank
-    gbs = 3 * D * esize * live / (ms * 1e-3) / 1e9
+    live = live_rows(masks, N_VIS) * n_sel            # rows streamed on THIS rank (2 reads + 1 write each)
+    padded = B * T * n_sel - live                     # padded text rows: never read, only their zero gradient is written
+    step_bytes = D * esize * (3 * live + padded)      # "only the zero-fill write counts"
+    gbs = step_bytes / (ms * 1e-3) / 1e9
     rec.update({"value": units / (ms * 1e-3), "ms_per_step": ms, "host_us_per_step": host_us,
-                "step_gbs_per_gpu": gbs, "frac": gbs / ctx.peak})
+                "step_gbs_per_gpu": gbs, "frac": gbs / ctx.peak, "algorithmic_bytes_per_step_per_gpu": step_bytes})
     if kernel_level:
         kms = kern_ms_m / steps
         rec.update({"kernel_level_ms_per_step": kms, "kernel_level_value": units / (kms * 1e-3),
@@ -593,7 +595,7 @@ def measure_point(ctx, n_sel, B, txt, D, dt, ragged, steps, warmup, loss="mse", 
         gms = graph_ms_m / steps
         rec.update({"graphed_ms_per_step": gms, "graphed_value": units / (gms * 1e-3),
                     "graphed_host_us_per_step": graph_host_us,
-                    "graphed_frac": 3 * D * esize * live / (gms * 1e-3) / 1e9 / ctx.peak})
+                    "graphed_frac": step_bytes / (gms * 1e-3) / 1e9 / ctx.peak})
         if kernel_level:
             rec["graphed_over_kernel"] = gms / (kern_ms_m / steps)
     del st, te, leaves, fd, loop
