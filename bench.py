@@ -603,19 +603,30 @@ def measure_point(ctx, n_sel, B, txt, D, dt, ragged, steps, warmup, loss="mse", 
 
 
 def c5_sweep(ctx, steps=40, warmup=8):
-    """BASELINE.json configs[4] / SURVEY 8(d) row C5: VLPythia-1B distillation, 15 layers, bf16, per-GPU batch
-    8..128 (global batch 8N..128N) x text 32 / 256 (visual:text 8:1 and 1:1) x all-ones / ragged masks."""
-    points = []
-    for B in (8, 16, 32, 64, 128):
+    """BASELINE.json configs[4] / SURVEY 8(d) row C5: VLPythia-1B distillation, 15 layers, bf16, per-GPU batch 8 ..
+    1024 / N (global batch up to 1024) x text 32 / 256 (visual:text 8:1 and 1:1) x all-ones / ragged masks (the
+    points of 256 samples per GPU and more: all-ones only, fewer steps, no graphed leg)."""
+    points, skipped = [], []
+    for B in (8, 16, 32, 64, 128, 256, 512, 1024):
+        if B * ctx.world > 1024:                      # configs[4]: global batch up to 1024
+            continue
         for txt in (32, 256):
-            for ragged in (False, True):
-                points.append(measure_point(ctx, 15, B, txt, 2048, "bf16", ragged, steps, warmup))
+            resident = 3 * 15 * B * (N_VIS + txt) * 2048 * 2          # student + teacher + gradients, bytes
+            if resident > 60e9:
+                skipped.append({"per_gpu_batch": B, "txt": txt, "resident_gb": resident / 1e9,
+                                "why": "left out to keep the default run's memory bounded (fits the 180 GB part)"})
+                continue
+            big = B >= 256
+            for ragged in ((False,) if big else (False, True)):
+                points.append(measure_point(ctx, 15, B, txt, 2048, "bf16", ragged, 12 if big else steps,
+                                            4 if big else warmup, graphed=not big))
     small = [p for p in points if p["per_gpu_batch"] == 8 and p["txt"] == 32 and p["mask"] == "all-ones"][0]
     return {"what": "VLPythia-1B (D=2048, 15 distilled layers, bf16): per-GPU batch x text length x mask through "
                     "fd.distill() + loss.backward() (`value`, `ms_per_step`; max over ranks), the same calls captured "
                     "into a CUDA graph and replayed (`graphed_*`), and the kernel-level loop (C-ABI calls from Python, "
                     "no autograd) beside them; GB/s per GPU on the 3*D*e basis over streamed rows",
-            "n_gpus": ctx.world, "steps": steps, "warmup": warmup, "points": points,
+            "n_gpus": ctx.world, "steps": steps, "warmup": warmup, "points": points, "skipped": skipped,
+            "global_batch_range": [8 * ctx.world, max(p["per_gpu_batch"] for p in points) * ctx.world],
             "smallest_point_api_over_kernel": small["api_over_kernel"],
             "smallest_point_graphed_over_kernel": small.get("graphed_over_kernel")}
 

@@ -17,8 +17,15 @@
 namespace mafed {
 namespace {
 
+// May this launch be a programmatic dependent of its predecessor in `stream`?  Not right behind a gate
+// (distill_gate.cu: the gate may have started a backward from the device that needs the SMs first).
+bool pdl_allowed(const mafed_shape_t& sh, void* stream) {
+  const bool after_gate = mafed_gate::consume_gate_mark(stream);
+  return tune(sh, kTuneNoPdl) == 0 && !after_gate;
+}
+
 HostLaunch host_launch(const mafed_shape_t& sh, void* stream) {
-  return HostLaunch{(cudaStream_t)stream, tune(sh, kTuneNoPdl) == 0};
+  return HostLaunch{(cudaStream_t)stream, pdl_allowed(sh, stream)};
 }
 
 // Arrival counters of the in-kernel tail (distill_tma.cuh).  A counter is zero whenever no kernel is using it
@@ -109,7 +116,7 @@ int launch_scalar_stage(const mafed_shape_t& sh, const mafed_weights_t* w, int f
   e.a.loss_kind = sh.loss_kind;
   e.a.flags = flags;
   if (w != nullptr) e.w = *w;
-  launch_pdl(k_epilogue, 1, kEpiThreads, 0, st, tune(sh, kTuneNoPdl) == 0, e);
+  launch_pdl(k_epilogue, 1, kEpiThreads, 0, st, pdl_allowed(sh, st), e);
   return (int)cudaPeekAtLastError();
 }
 
@@ -353,7 +360,7 @@ int mafed_distill_prefetch_counts(const mafed_shape_t* shape, const int64_t* att
   pp.n_vis_rows = vis_rows(*shape);
   pp.ticket = reinterpret_cast<long long*>(ticket);
   pp.comm = comm_dev(comm);
-  launch_pdl(k_prefetch_counts, 1, kEpiThreads, 0, (cudaStream_t)stream, tune(*shape, kTuneNoPdl) == 0, pp);
+  launch_pdl(k_prefetch_counts, 1, kEpiThreads, 0, (cudaStream_t)stream, pdl_allowed(*shape, stream), pp);
   return (int)cudaPeekAtLastError();
 }
 
@@ -460,7 +467,7 @@ int mafed_distill_modality_masks(const mafed_shape_t* shape, const int64_t* attn
   if (!lang_mask || !image_mask || (needs_mask(*shape) && !attn_mask)) return MAFED_E_ARG;
   const long long n = (long long)shape->B * shape->T;
   const unsigned grid = (unsigned)clamp_grid((n + 255) / 256, 1 << 20);
-  launch_pdl(k_modality_masks, grid > 1184 ? 1184u : grid, 256, 0, (cudaStream_t)stream, tune(*shape, kTuneNoPdl) == 0,
+  launch_pdl(k_modality_masks, grid > 1184 ? 1184u : grid, 256, 0, (cudaStream_t)stream, pdl_allowed(*shape, stream),
              attn_mask, lang_mask, image_mask, n, (int)shape->T, (int)shape->n_vis);
   return (int)cudaPeekAtLastError();
 }

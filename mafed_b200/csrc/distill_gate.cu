@@ -17,6 +17,7 @@
 #define MAFED_DEVICE_LAUNCH 1
 #include "distill_gate.h"
 
+#include <atomic>
 #include <type_traits>
 
 #include "distill_dispatch.cuh"
@@ -72,6 +73,39 @@ struct GateLaunch {
 
 }  // namespace
 
+// The kernel that follows a gate in its stream must not be a programmatic dependent of it.  A dependent launch may
+// become resident as soon as the gate's single block has exited -- while the backward the gate started from the
+// device is still waiting to be scheduled -- and a resident persistent grid (one CTA per SM, most of the shared
+// memory each) blocked in griddepcontrol.wait would then hold exactly the resources that backward needs: the
+// dependent waits for the gate's grid (children included) to complete, the child waits for an SM.  So the library
+// remembers the streams a gate went to and launches its next kernel there fully serialised (the only cost: that
+// kernel's launch latency is not hidden behind a 2 us gate; kernels of other libraries are not programmatic launches).
+namespace {
+constexpr int kGateMarks = 16;
+std::atomic<uintptr_t> g_gate_marks[kGateMarks];
+inline uintptr_t stream_key(void* stream) { return reinterpret_cast<uintptr_t>(stream) + 1; }   // 0 = empty slot
+}  // namespace
+
+void note_gate_launch(void* stream) {
+  const uintptr_t key = stream_key(stream);
+  for (auto& m : g_gate_marks)
+    if (m.load(std::memory_order_relaxed) == key) return;
+  for (auto& m : g_gate_marks) {
+    uintptr_t empty = 0;
+    if (m.compare_exchange_strong(empty, key)) return;
+  }
+  g_gate_marks[key % kGateMarks].store(key);     // table full: overwrite (the displaced stream loses only its mark)
+}
+
+bool consume_gate_mark(void* stream) {
+  const uintptr_t key = stream_key(stream);
+  for (auto& m : g_gate_marks) {
+    uintptr_t expect = key;
+    if (m.load(std::memory_order_relaxed) == key && m.compare_exchange_strong(expect, 0)) return true;
+  }
+  return false;
+}
+
 int gated_backward(const mafed_shape_t* shape, const void* const* student_ptrs, const void* const* teacher_ptrs,
                    void* const* grad_ptrs, const int64_t* attn_mask, const float* bwd_scale, const float* grad_out,
                    float grad_out_scale, float assumed, float* grad_out_seen, void* stream) {
@@ -82,8 +116,11 @@ int gated_backward(const mafed_shape_t* shape, const void* const* student_ptrs, 
   p.grad_out = grad_out;       // the started kernel reads the upstream gradient itself
   p.gout_scale = grad_out_scale;
   p.reverse = tune(*shape, kTuneBwdForward) ? 0 : 1;
-  GateLaunch go{(cudaStream_t)stream, tune(*shape, kTuneNoPdl) == 0, GateArgs{grad_out, grad_out_scale, assumed, grad_out_seen, 0, 0, 0}};
-  return dispatch<kPassBwd>(*shape, p, go);
+  const bool pdl = tune(*shape, kTuneNoPdl) == 0 && !consume_gate_mark(stream);   // (a gate right behind a gate)
+  GateLaunch go{(cudaStream_t)stream, pdl, GateArgs{grad_out, grad_out_scale, assumed, grad_out_seen, 0, 0, 0}};
+  rc = dispatch<kPassBwd>(*shape, p, go);
+  note_gate_launch(stream);
+  return rc;
 }
 
 }  // namespace mafed_gate

@@ -11,4 +11,9 @@ int gated_backward(const mafed_shape_t* shape, const void* const* student_ptrs, 
                    void* const* grad_ptrs, const int64_t* attn_mask, const float* bwd_scale, const float* grad_out,
                    float grad_out_scale, float assumed, float* grad_out_seen, void* stream);
 
+// Ordering latch (see distill_gate.cu): every launch of the library asks `consume_gate_mark(stream)` and, if a gate
+// was the last thing it sent to that stream, launches without the programmatic-dependent-launch attribute.
+void note_gate_launch(void* stream);
+bool consume_gate_mark(void* stream);
+
 }  // namespace mafed_gate

@@ -31,8 +31,8 @@ def test_graphed_step_equals_eager_step_and_takes_new_data(loss_kind, dtype):
     meta = dict(META, loss=loss_kind)
     st, te, am = O.make_inputs(4, 3, 6, 768, n_vis=256, dtype=dtype, seed=31)
     fd = make_method(meta)
-    step = GraphedDistillStep(fd, [s.cuda() for s in st], [t.cuda() for t in te], am.cuda().clone())
-    assert step.layers == [0, 1, 2]
+    step = fd.capture([s.cuda() for s in st], [t.cuda() for t in te], am.cuda().clone())
+    assert isinstance(step, GraphedDistillStep) and step.layers == [0, 1, 2]
     for trial, seed in enumerate((31, 32, 33)):
         st2, te2, am2 = O.make_inputs(4, 3, 6, 768, n_vis=256, dtype=dtype, seed=seed,
                                       teacher="close" if trial != 1 else "independent")
@@ -67,7 +67,7 @@ def test_gate_starts_the_backward_from_the_device_inside_a_replay():
     fd.adapt_assumed_grad_out = False
     assert fd.assumed_grad_out == 1.0
     step = GraphedDistillStep(fd, [s.cuda() for s in st], [t.cuda() for t in te], am.cuda().clone(), grad_out=0.25)
-    for _ in range(3):
+    for _ in range(20):
         step.replay()
     torch.cuda.synchronize()
     ref = O.forward_backward(st, te, am, oracle_cfg(META), grad_out=0.25)
@@ -103,3 +103,56 @@ def test_assumed_upstream_gradient_follows_what_the_gate_sees():
     (fd.distill(Out(tuple(leaves)), {"attention_mask": am.cuda()}) * 0.125).backward()
     for l in range(3):
         assert rel_err(leaves[l].grad.cpu(), ref["grads"][l]) < 1e-5
+
+
+def test_steps_back_to_back_behind_a_gate_that_starts_the_backward():
+    """Kernel-level steps enqueued back to back (no host gap), every gate finding a mismatch and starting the backward
+    from the device: the next step's fused kernel must not become resident ahead of that backward (the library
+    launches the kernel that follows a gate without the programmatic-dependent-launch attribute).  Eager and as two
+    steps inside ONE captured graph."""
+    from mafed_b200 import cabi
+    from mafed_b200.distill_op import DistillPlan, distill_backward, distill_fused
+    cfg = oracle_cfg(META)
+    layers, coeffs, _ = O.layer_plan(cfg)
+    plan = DistillPlan(layers=layers, layer_coeffs=[float(c) for c in coeffs], modality_kind=cabi.MODW_TABLE,
+                       lang_weights=[0.5] * len(layers))
+    st, te, am = O.make_inputs(4, 6, 9, 2048, n_vis=256, dtype=torch.bfloat16, seed=47)
+    s = [x.cuda() for x in st[:3]]
+    t = [x.cuda() for x in te[:3]]
+    mask = am.cuda()
+    gout = torch.full((), 0.5, device="cuda")
+    ref = O.forward_backward(st, te, am, cfg, grad_out=0.5)
+
+    def step(g):
+        out, scale, ln = distill_fused(s, t, g, mask, plan, group=False)       # assumes an upstream gradient of 1
+        distill_backward(ln, g, scale, gout, skip_if_equals=1.0)               # ... finds 0.5: exact backward
+        return out
+
+    def check(g):
+        torch.cuda.synchronize()
+        for l in range(3):
+            assert rel_err(g[l].float().cpu(), ref["grads"][l].float()) < 2e-3
+
+    g1 = [torch.empty_like(x) for x in s]
+    g2 = [torch.empty_like(x) for x in s]
+    for i in range(200):
+        step(g1 if i % 2 == 0 else g2)
+    check(g1)
+    check(g2)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(g1)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    for g in (g1, g2):
+        for x in g:
+            x.zero_()
+    with torch.cuda.graph(graph):
+        step(g1)
+        step(g2)
+    for _ in range(50):
+        graph.replay()
+    check(g1)
+    check(g2)
