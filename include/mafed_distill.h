@@ -30,7 +30,9 @@
  * launch; without one the stages are available separately for an NCCL sequence:
  * mafed_distill_fwd | mafed_distill_fused -> mafed_distill_scalar_stage(REDUCE|COUNTS) -> allreduce(sums) ->
  * mafed_distill_scalar_stage(LOSSES|SCALE).
- * The library keeps no process-global mutable state: experiment knobs travel with the call (mafed_shape_t::tuning).
+ * The library has no process-global knobs: experiment knobs travel with the call (mafed_shape_t::tuning).  What it
+ * remembers between calls is bookkeeping only (per-device attribute caches, the round-robin index of its arrival
+ * counters, and which streams a gate was last sent to -- see mafed_distill_bwd).
  */
 #ifndef MAFED_DISTILL_H_
 #define MAFED_DISTILL_H_
@@ -170,7 +172,9 @@ int mafed_distill_fwd_step(const mafed_shape_t* shape, const void* const* studen
  * launch compares g with *skip_if_equals on the device and returns at once when they match (the gradients of
  * mafed_distill_step are already right); otherwise it starts the backward itself, stream-ordered behind it
  * (device-side tail launch).  `grad_out_seen` (optional, device-accessible, e.g. pinned host memory) receives g,
- * so that a caller can learn the upstream gradient its steps really get without synchronising. */
+ * so that a caller can learn the upstream gradient its steps really get without synchronising.  The kernel this
+ * library sends to `stream` right after a gate is launched without the programmatic-dependent-launch attribute, so
+ * that it cannot occupy the SMs before a backward the gate started. */
 int mafed_distill_bwd(const mafed_shape_t* shape, const void* const* student_ptrs,
                       const void* const* teacher_ptrs, void* const* grad_ptrs, const int64_t* attn_mask,
                       const float* bwd_scale, const float* grad_out, float grad_out_scale,

@@ -1,9 +1,10 @@
 """Peer-memory communicator for the batch-sharded step (one process per GPU, one NVLink box).
 
 `torch.distributed` is only the plumbing here: it carries the 64-byte CUDA IPC handles once, at set-up.
-After that the per-step exchange (<= 2L+2 doubles) happens inside the single-CTA scalar-stage kernel with
-NVLink peer stores and flags (``csrc/distill_comm.cuh``) -- no NCCL call and no extra launch on the step's
-critical path.  If the ranks are not on one host, or a mailbox cannot be mapped, every rank falls back to
+After that the per-step exchanges (<= 2L+2 doubles) happen inside the path's own kernels with NVLink peer stores
+of self-validating words (``csrc/distill_comm.cuh``): the token counts leave when the batch is drawn
+(``prefetch_counts``), the sums are exchanged by the fused kernel's last CTA -- no NCCL call and no extra launch on
+the step's critical path.  If the ranks are not on one host, or a mailbox cannot be mapped, every rank falls back to
 the NCCL allreduce together.
 """
 from __future__ import annotations
