@@ -618,8 +618,12 @@ def c5_sweep(ctx, steps=40, warmup=8):
                 continue
             big = B >= 256
             for ragged in ((False,) if big else (False, True)):
-                points.append(measure_point(ctx, 15, B, txt, 2048, "bf16", ragged, 12 if big else steps,
-                                            4 if big else warmup, graphed=not big))
+                try:
+                    points.append(measure_point(ctx, 15, B, txt, 2048, "bf16", ragged, 12 if big else steps,
+                                                4 if big else warmup, graphed=not big))
+                except torch.cuda.OutOfMemoryError as exc:      # (a smaller part, or memory held by a neighbour)
+                    skipped.append({"per_gpu_batch": B, "txt": txt, "why": "out of memory: " + str(exc)[:80]})
+                    torch.cuda.empty_cache()
     small = [p for p in points if p["per_gpu_batch"] == 8 and p["txt"] == 32 and p["mask"] == "all-ones"][0]
     return {"what": "VLPythia-1B (D=2048, 15 distilled layers, bf16): per-GPU batch x text length x mask through "
                     "fd.distill() + loss.backward() (`value`, `ms_per_step`; max over ranks), the same calls captured "

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from mafed_b200 import cabi
+from mafed_b200 import comm as _comm
 from mafed_b200.capture import HiddenStateCapture
 from mafed_b200.distill_op import DistillPlan, distill_loss, modality_masks, resolve_group, seen_slot
 from mafed_b200.methods.base import CLStrategy
@@ -357,8 +358,9 @@ class FeatureDistillation(CLStrategy):
                 states = cap.hidden_states
             else:
                 states = self.past_model(**batch, output_hidden_states=True, return_dict=True).hidden_states
-        return [states[l] if states[l].grad_fn is None and not states[l].requires_grad else states[l].detach()
-                for l in layers]
+        # no per-tensor `.detach()` (distillation.py:223): these come out of a no_grad forward, and the node never builds
+        # a graph edge to a teacher tensor whatever its flags are
+        return [states[l] for l in layers]
 
     def _get_past_hidden_states(self, batch):
         with torch.no_grad():
@@ -402,7 +404,8 @@ class FeatureDistillation(CLStrategy):
         are logged, in order: a step whose copy has not completed yet stays queued."""
         self.last_layer_losses = aux
         self.last_layers = list(layers)
-        self.check_exchange(sync=False)
+        if self.process_group is not False and _comm._cache:
+            self.check_exchange(sync=False)
         if _wandb is None or getattr(_wandb, "run", None) is None:
             return
         if torch.cuda.is_current_stream_capturing():
@@ -440,11 +443,10 @@ class FeatureDistillation(CLStrategy):
         memory, so reading it costs nothing: ``distill`` does it every step (``sync=False``: it sees every step
         that has FINISHED, i.e. a missed exchange raises one step late at the latest, before the poisoned
         gradients can survive an optimizer step unnoticed); ``sync=True`` waits for the queued steps first."""
-        from mafed_b200.comm import peek_peer_comm
         group = self.process_group
         if group is False:
             return
-        peer = peek_peer_comm(None if group is None or group is True else group)
+        peer = _comm.peek_peer_comm(None if group is None or group is True else group)
         if peer is not None:
             if sync:
                 torch.cuda.synchronize()
