@@ -894,8 +894,25 @@ def run_main(ctx):
     if world > 1:
         uncoupled_after = uncoupled_loop()
         uncoupled = [0.5 * (a + b) for a, b in zip(uncoupled_before, uncoupled_after)]
-    api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms = ctx.max_over_ranks(
-        [api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms])
+    # the same two API calls captured once into a CUDA graph and replayed (fd.capture): the host side of a step that
+    # is part of a graphed training step
+    gstep = make_method(n_sel).capture(st, te, masks[0])
+    for _ in range(args.warmup):
+        gstep.replay()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.sync_all()
+    t_host = time.perf_counter()
+    g0.record()
+    for _ in range(args.steps):
+        gstep.replay()
+    g1.record()
+    graph_host_us = (time.perf_counter() - t_host) / args.steps * 1e6
+    ctx.sync_all()
+    graph_ms = g0.elapsed_time(g1)
+    graph_loss = float(gstep.loss)
+    del gstep
+    api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms, graph_ms = ctx.max_over_ranks(
+        [api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms, graph_ms])
     ms_per_step = api_ms / args.steps
     value = units_per_step / (ms_per_step * 1e-3)
 
@@ -936,6 +953,9 @@ def run_main(ctx):
                           "frac_of_nominal_8000": gbs(fused_bytes, ms_per_step) / 8000.0, "bytes_per_unit": 3 * row_bytes},
         "kernel_value": units_per_step / (one_raw_ms / args.steps * 1e-3),
         "host_us_per_step": host_us,
+        "graphed": {"what": "fd.capture(...): distill() + backward() captured once into a CUDA graph, replayed per step",
+                    "ms_per_step": graph_ms / args.steps, "value": units_per_step / (graph_ms / args.steps * 1e-3),
+                    "host_us_per_step": graph_host_us, "loss": graph_loss},
         "kernel_level_step_ms": {"one_pass": step_stats.get("one_pass_step"), "two_pass": step_stats.get("two_pass_step")},
         "two_pass": {
             "note": "north_star's two-kernel form (fused forward, then fused backward): 5*D*e bytes per token*layer",
