@@ -864,9 +864,18 @@ def run_main(ctx):
             e1.record()
             torch.cuda.synchronize()
         return e0.elapsed_time(e1) / args.steps
-    base_ms = min(plain_loop(None) for _ in range(2))
-    gate_loop_ms = min(plain_loop("gate") for _ in range(2))
-    full_loop_ms = min(plain_loop("full_grid") for _ in range(2))
+    # (interleaved rounds, differences taken inside a round: under a power cap the step time drifts by a few percent
+    #  over a second, which is more than what is being measured here)
+    ab_rounds = []
+    for _ in range(3):
+        ab_rounds.append([plain_loop(None), plain_loop("gate"), plain_loop("full_grid"),
+                          loop.timed(args.steps, args.warmup)[0] / args.steps])
+    base_ms = statistics.median(r[0] for r in ab_rounds)
+    gate_loop_ms = statistics.median(r[1] for r in ab_rounds)
+    full_loop_ms = statistics.median(r[2] for r in ab_rounds)
+    gate_us = statistics.median(r[1] - r[0] for r in ab_rounds) * 1e3
+    full_grid_us = statistics.median(r[2] - r[0] for r in ab_rounds) * 1e3
+    api_minus_kernel_us = statistics.median(r[3] - r[1] for r in ab_rounds) * 1e3
 
     # ---- (2) the public API: the headline `value`
     fd.single_pass = False
@@ -940,13 +949,15 @@ def run_main(ctx):
                      "achieved": gbs(fused_bytes, fused_ms), "peak": peak, "unit": "GB/s",
                      "frac": gbs(fused_bytes, fused_ms) / peak, "traffic": measured_traffic(wl), "peak_source": peak_src,
                      "bytes_per_launch": fused_bytes, "bytes_per_unit": 3 * row_bytes, "ms_per_launch": fused_ms,
-                     "gate_launch_ms": max(0.0, gate_loop_ms - base_ms), "fixup_launch_ms": max(0.0, gate_loop_ms - base_ms),
+                     "gate_launch_ms": max(0.0, gate_us * 1e-3), "fixup_launch_ms": max(0.0, gate_us * 1e-3),
                      "gate": {"what": "per-step cost of checking the upstream gradient in backward, from back-to-back "
                                       "kernel-level steps on this rank: fused kernel alone / + 1-CTA gate (the product) "
-                                      "/ + the full persistent grid that returns at once (round 1)",
+                                      "/ + the full persistent grid that returns at once (round 1); three interleaved "
+                                      "rounds, median of the in-round differences",
                               "fused_only_ms_per_step": base_ms, "with_gate_ms_per_step": gate_loop_ms,
                               "with_full_grid_fixup_ms_per_step": full_loop_ms,
-                              "gate_us": (gate_loop_ms - base_ms) * 1e3, "full_grid_us": (full_loop_ms - base_ms) * 1e3,
+                              "gate_us": gate_us, "full_grid_us": full_grid_us,
+                              "rounds_ms": [r[:3] for r in ab_rounds],
                               "gate_event_pair_ms": gate_ms}},
         "roofline_step": {"achieved": gbs(fused_bytes, ms_per_step), "peak": peak, "unit": "GB/s",
                           "frac": gbs(fused_bytes, ms_per_step) / peak,
@@ -1000,7 +1011,8 @@ def run_main(ctx):
                                   "the slowest GPU every step: ms_per_step vs max(uncoupled) is the cost of the exchange "
                                   "itself, max(uncoupled) vs the 1-GPU run is GPU-to-GPU variation")
     line["clocks"] = sampler.summary()
-    line["api_minus_kernel_loop_us"] = (ms_per_step - gate_loop_ms) * 1e3 if world == 1 else None
+    # the API loop against the kernel-level loop (fused + gate), same interleaved rounds
+    line["api_minus_kernel_loop_us"] = api_minus_kernel_us if world == 1 else None
 
     if not args.no_c5:
         try:

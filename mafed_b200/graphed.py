@@ -6,7 +6,7 @@ device thread costs the host 100-150 us per step -- more than the kernels of a s
 configs[4]: 8 samples per GPU is ~80 us of HBM traffic).  Every piece of the step is capture-safe: no host
 synchronisation, no host-side epoch (the exchange counters live on the device), allocations through torch's
 caching allocator.  So a trainer that captures its whole training step with ``torch.cuda.graph`` gets the
-distillation term for a graph replay's ~10 us of host time; ``GraphedDistillStep`` is that capture for the path
+distillation term for a graph replay's ~4 us of host time; ``GraphedDistillStep`` is that capture for the path
 alone, over static hidden-state buffers: copy new activations into ``students`` / ``teachers`` / ``attention_mask``
 (or let the producing kernels write there), ``replay()``, read ``loss`` / ``grads``.
 """
