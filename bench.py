@@ -604,20 +604,21 @@ def measure_point(ctx, n_sel, B, txt, D, dt, ragged, steps, warmup, loss="mse", 
 
 def c5_sweep(ctx, steps=40, warmup=8):
     """BASELINE.json configs[4] / SURVEY 8(d) row C5: VLPythia-1B distillation, 15 layers, bf16, per-GPU batch 8 ..
-    1024 / N (global batch up to 1024) x text 32 / 256 (visual:text 8:1 and 1:1) x all-ones / ragged masks (the
-    points of 256 samples per GPU and more: all-ones only, fewer steps, no graphed leg)."""
+    1024 / N (global batch up to 1024) x text 32 / 64 / 128 / 256 (visual:text 8:1 .. 1:1) x all-ones / ragged masks
+    (ragged at text 32 and 256; the points of 256 samples per GPU and more: all-ones only, fewer steps, no graphed
+    leg)."""
     points, skipped = [], []
     for B in (8, 16, 32, 64, 128, 256, 512, 1024):
         if B * ctx.world > 1024:                      # configs[4]: global batch up to 1024
             continue
-        for txt in (32, 256):
+        for txt in (32, 64, 128, 256):
             resident = 3 * 15 * B * (N_VIS + txt) * 2048 * 2          # student + teacher + gradients, bytes
             if resident > 60e9:
                 skipped.append({"per_gpu_batch": B, "txt": txt, "resident_gb": resident / 1e9,
                                 "why": "left out to keep the default run's memory bounded (fits the 180 GB part)"})
                 continue
             big = B >= 256
-            for ragged in ((False,) if big else (False, True)):
+            for ragged in ((False,) if big or txt in (64, 128) else (False, True)):
                 try:
                     points.append(measure_point(ctx, 15, B, txt, 2048, "bf16", ragged, 12 if big else steps,
                                                 4 if big else warmup, graphed=not big))

@@ -26,6 +26,7 @@ TUNE_NO_PDL = 15
 TUNE_NO_INLINE_SCALE, TUNE_NO_TAIL = 16, 17   # 1: separate prologue launch / separate epilogue launch
 TUNE_VARIANT_ALL = 18                          # kernel family of every pass: 1 ldg, 2 tma (0 = default)
 TUNE_NO_GATE = 19                              # 1: backward fix-up as a full grid that returns at once (round-1 form)
+TUNE_PACE_NS = 20                              # TMA producer: nanoseconds between a free slot and its refill (experiment)
 N_TUNE_KEYS = 24
 
 # MAFED_B200_LIB: another build of the same C ABI (A/B measurements of two kernel versions, tools/ab_lib.py)

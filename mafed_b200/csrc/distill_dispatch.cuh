@@ -22,7 +22,8 @@ constexpr int kMaxDevices = 64;
 // keys of mafed_tuning_t::v (see include/mafed_distill.h); the first three are per pass: key + Pass
 enum TuneKey { kTuneTmaStages = 0, kTuneTmaRows = 3, kTuneVariant = 6, kTuneTmaWarps = 9, kTuneLdgBlocksPerSm = 10,
                kTuneBwdForward = 11, kTuneGridMul = 12, kTuneLoadPolicy = 13, kTuneStorePolicy = 14, kTuneNoPdl = 15,
-               kTuneNoInlineScale = 16, kTuneNoTail = 17, kTuneVariantAll = 18, kTuneNoGate = 19 };
+               kTuneNoInlineScale = 16, kTuneNoTail = 17, kTuneVariantAll = 18, kTuneNoGate = 19,
+               kTunePaceNs = 20 };
 
 inline int tune(const mafed_shape_t& sh, int key) { return sh.tuning != nullptr ? sh.tuning->v[key] : 0; }
 
@@ -261,17 +262,26 @@ inline bool tma_geometry(const mafed_shape_t& sh, const PathParams& p, int pass,
   if (row_bytes > 32768) return false;
   const long long budget = (long long)dv.smem_optin - 16 * 1024;  // static smem + slack
   int rows = tune(sh, kTuneTmaRows + pass);
-  bool cosine_fine = false;
+  const bool rows_default = rows <= 0, stages_default = tune(sh, kTuneTmaStages + pass) <= 0;
+  bool cosine_fine = false, fused_fine = false;
   if (rows <= 0) {
-    // Measured on B200 (profiles/r01_call3_sweep_step.json): a ring of 2 stages x 64-72 KB per SM is the
-    // sweet spot for every pass; deeper rings (>= 192 KB in flight per SM) cost 4-8 % of HBM throughput.
+    // Measured on B200.  Forward and backward passes (profiles/r01_call3_sweep_step.json): 2 stages x 64-72 KB per
+    // SM; deeper rings (>= 192 KB in flight per SM) cost 4-8 % of HBM throughput.
     // The cosine gradient needs two sweeps over a row with a warp reduction in between, so a stage drains more
-    // slowly: with rows >= 4 KB a finer ring (4 stages x 32 KB) keeps more rows in different phases at once --
-    // 5-8 % faster on the 1B shape on two boxes (profiles/r01b_sweep_ring*.json), neutral or worse for short rows.
-    cosine_fine = loss == MAFED_LOSS_COSINE && pass != kPassFwd && row_bytes >= 4096;
-    const long long stage_target = cosine_fine ? 32 * 1024 : 72 * 1024;
+    // slowly: a finer ring (4 stages x 32 KB) keeps more rows in different phases at once.
+    // The one-pass step (profiles/r02l_geometry_sweep.txt, 13 shapes x 13 rings, after the producer stopped paying
+    // 64-bit divisions and the mask round trip per tile): 3 stages x 32 KB (96 KB in flight per SM) is the best or
+    // within 1.5 % of it for every shape of 256 visual + ~32 text rows (base / 410M / 1B, bf16 and fp32, 16..256
+    // samples), 5-9 % ahead of 2 x 64 KB; 64 KB in flight is latency-bound (+20 %), 128 KB and more queue up in the
+    // memory system (+5-13 %).  Text-heavy batches (more than a quarter of the rows behind the attention mask, where
+    // ragged masks make whole tiles zero-fill only) keep the coarse ring: fewer, larger tiles amortise the per-tile
+    // cost of the padded ones (32 KB x 3 is 4-14 % behind there).
+    cosine_fine = loss == MAFED_LOSS_COSINE && pass != kPassFwd && (row_bytes >= 4096 || pass == kPassFused);
+    const bool text_heavy = (long long)(sh.T - sh.n_vis) * 4 > (long long)sh.T;
+    fused_fine = !cosine_fine && pass == kPassFused && !text_heavy;
+    const long long stage_target = (cosine_fine || fused_fine) ? 32 * 1024 : 72 * 1024;
     rows = (int)(stage_target / (2 * row_bytes));
-    if (rows >= 8) rows &= ~7;
+    if (rows >= 8 && !fused_fine && !(cosine_fine && pass == kPassFused)) rows &= ~7;
   }
   if (rows > kTmaMaxRows) rows = kTmaMaxRows;
   if (rows < 1) rows = 1;
@@ -280,10 +290,21 @@ inline bool tma_geometry(const mafed_shape_t& sh, const PathParams& p, int pass,
   geo.rows = rows;
   geo.stage_bytes = (int)(2 * rows * row_bytes);
   int stages = tune(sh, kTuneTmaStages + pass);
-  if (stages <= 0) stages = cosine_fine ? 4 : ((2 * geo.stage_bytes >= 96 * 1024) ? 2 : 3);
+  if (stages <= 0) stages = cosine_fine ? 4 : (fused_fine ? 3 : ((2 * geo.stage_bytes >= 96 * 1024) ? 2 : 3));
   if (stages > kTmaMaxStages) stages = kTmaMaxStages;
   while (stages > 1 && (long long)stages * geo.stage_bytes > budget) --stages;
   geo.stages = stages;
+  // Refill pacing (profiles/r02n_pace_sweep.txt).  The coarse ring of a text-heavy one-pass step, every row live:
+  // 0.96 ms refilled at once, 0.90 ms with ~0.5 us between a free slot and its refill (in-flight bytes per SM are
+  // what the memory system is sensitive to); with a ragged mask the same pause costs 4 %, so the producer drops it
+  // at the first padded row it meets.  kTunePaceNs: > 0 explicit (unconditional), < 0 off.
+  const int pace = tune(sh, kTunePaceNs);
+  geo.pace_ns = pace > 0 ? pace : 0;
+  geo.pace_dense = 0;
+  if (pace == 0 && pass == kPassFused && !fused_fine && !cosine_fine && rows_default && stages_default) {
+    geo.pace_ns = 500;
+    geo.pace_dense = 1;
+  }
   return true;
 }
 

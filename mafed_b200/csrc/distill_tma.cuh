@@ -16,6 +16,8 @@ struct TmaGeom {
   int stages;
   int rows;         // rows per stage
   int stage_bytes;  // 2 * rows * row_bytes
+  int pace_ns;      // producer: pause between a slot becoming free and its refill (0: none)
+  int pace_dense;   // 1: only while this CTA has met no padded row yet (the batch looks dense)
 };
 
 struct TmaStageMeta {
@@ -85,17 +87,55 @@ __device__ __forceinline__ void tma_producer(const PathParams& p, const TmaGeom&
   const uint64_t lpol = make_policy(p.load_policy);
   int stage = 0;
   uint32_t phase = 0;
+  // The row weights of a tile come from the attention mask (an L2 round trip).  They are fetched one tile ahead, so
+  // that the trip overlaps the wait for a free slot: a run of padded tiles (long, half-empty text) is otherwise paced
+  // by this warp's load latency instead of by the zero-fill's bandwidth.
+  struct Tile { int l, n_rows, m; long long row0; float w; };
+  // (layer, tile in layer) of this CTA's tiles advance by gridDim.x per step: kept incrementally, no 64-bit division
+  // on the per-tile path; the row -> (sample, position) split is a 32-bit division whenever the row count allows it
+  const bool rows32 = p.n_rows <= 0x7fffffffLL;
+  int f_l = (int)((long long)blockIdx.x / tiles_per_layer);
+  long long f_til = (long long)blockIdx.x - (long long)f_l * tiles_per_layer;
+  auto fetch = [&]() {
+    Tile x;
+    x.l = p.reverse ? (p.n_layers - 1 - f_l) : f_l;
+    x.row0 = (p.reverse ? (tiles_per_layer - 1 - f_til) : f_til) * geo.rows;
+    x.n_rows = (int)min((long long)geo.rows, p.n_rows - x.row0);
+    x.m = 1;
+    x.w = 0.f;
+    if (lane < x.n_rows) {
+      if (rows32) {
+        const unsigned row = (unsigned)x.row0 + (unsigned)lane;
+        const unsigned bb = row / (unsigned)p.T;
+        const int t = (int)(row - bb * (unsigned)p.T);
+        if (t < p.n_vis) x.w = 1.f;
+        else { x.m = 0; x.w = (float)__ldg(p.mask + (long long)bb * p.txt + (t - p.n_vis)); }
+      } else {
+        x.w = row_weight(p, x.row0 + lane, x.m);
+      }
+    }
+    if (for_backward && p.g[x.l] == nullptr) x.w = 0.f;
+    f_til += gridDim.x;
+    while (f_til >= tiles_per_layer) { f_til -= tiles_per_layer; ++f_l; }
+    return x;
+  };
+  Tile next = {};
+  bool seen_padded = false;
+  if ((long long)blockIdx.x < total) next = fetch();
   for (long long t0 = blockIdx.x; t0 < total; t0 += gridDim.x) {
-    const long long tile = p.reverse ? (total - 1 - t0) : t0;
-    const int l = (int)(tile / tiles_per_layer);
-    const long long row0 = (tile - (long long)l * tiles_per_layer) * geo.rows;
-    const int n_rows = (int)min((long long)geo.rows, p.n_rows - row0);
+    const Tile cur = next;
+    if (t0 + gridDim.x < total) next = fetch();
+    const int l = cur.l, n_rows = cur.n_rows, m = cur.m;
+    const long long row0 = cur.row0;
+    const float w = cur.w;
     mbar_wait(smem_u32(&empty[stage]), phase ^ 1u);  // slot free (first lap passes immediately)
+    // Pacing (see tma_geometry): with every row live the step is bound by DRAM, and a coarse ring refilled at once
+    // queues more in the memory system than it can use; with padded rows about, the CTAs holding more live rows are
+    // the critical path and must not be held back.
+    if (lane < n_rows && w == 0.f) seen_padded = true;
+    seen_padded = __any_sync(0xffffffffu, seen_padded);
+    if (geo.pace_ns > 0 && !(geo.pace_dense && seen_padded)) __nanosleep((unsigned)geo.pace_ns);
 
-    int m = 1;
-    float w = 0.f;
-    if (lane < n_rows) w = row_weight(p, row0 + lane, m);
-    if (for_backward && p.g[l] == nullptr) w = 0.f;
     const unsigned valid = __ballot_sync(0xffffffffu, w != 0.f);
     TmaStageMeta& mt = meta[stage];
     mt.w[lane] = w;

@@ -50,6 +50,24 @@ def main():
 
     print(f"{wl}: {timeit(step):.1f} us of host time per step (distill + backward, enqueue only)")
 
+    with torch.autograd.set_multithreading_enabled(False):
+        print(f"  the same step with torch.autograd.set_multithreading_enabled(False) (engine runs the nodes on the "
+              f"calling thread, no hand-off to the device thread): {timeit(step):.1f} us")
+
+    # marginal cost inside a larger backward: a step whose loss also has another term over the same leaves, with and
+    # without the distillation term
+    def other_only():
+        for s in leaves:
+            s.grad = None
+        (leaves[0][0, 0, 0] * 2.0).backward()
+
+    def other_plus_distill():
+        for s in leaves:
+            s.grad = None
+        (leaves[0][0, 0, 0] * 2.0 + fd.distill(out, batch)).backward()
+    a, b = timeit(other_only), timeit(other_plus_distill)
+    print(f"  marginal: (other + distill).backward() {b:.1f} us - other.backward() {a:.1f} us = {b - a:.1f} us")
+
     def fwd_only():
         fd.distill(out, batch)
     print(f"  fd.distill() alone (graph dropped, no backward):     {timeit(fwd_only):.1f} us")
