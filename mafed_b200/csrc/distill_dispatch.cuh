@@ -263,25 +263,29 @@ inline bool tma_geometry(const mafed_shape_t& sh, const PathParams& p, int pass,
   const long long budget = (long long)dv.smem_optin - 16 * 1024;  // static smem + slack
   int rows = tune(sh, kTuneTmaRows + pass);
   const bool rows_default = rows <= 0, stages_default = tune(sh, kTuneTmaStages + pass) <= 0;
-  bool cosine_fine = false, fused_fine = false;
+  bool cosine_fine = false, fused_fine = false, wide = false;
   if (rows <= 0) {
-    // Measured on B200.  Forward and backward passes (profiles/r01_call3_sweep_step.json): 2 stages x 64-72 KB per
-    // SM; deeper rings (>= 192 KB in flight per SM) cost 4-8 % of HBM throughput.
-    // The cosine gradient needs two sweeps over a row with a warp reduction in between, so a stage drains more
-    // slowly: a finer ring (4 stages x 32 KB) keeps more rows in different phases at once.
-    // The one-pass step (profiles/r02l_geometry_sweep.txt, 13 shapes x 13 rings, after the producer stopped paying
-    // 64-bit divisions and the mask round trip per tile): 3 stages x 32 KB (96 KB in flight per SM) is the best or
-    // within 1.5 % of it for every shape of 256 visual + ~32 text rows (base / 410M / 1B, bf16 and fp32, 16..256
-    // samples), 5-9 % ahead of 2 x 64 KB; 64 KB in flight is latency-bound (+20 %), 128 KB and more queue up in the
-    // memory system (+5-13 %).  Text-heavy batches (more than a quarter of the rows behind the attention mask, where
-    // ragged masks make whole tiles zero-fill only) keep the coarse ring: fewer, larger tiles amortise the per-tile
-    // cost of the padded ones (32 KB x 3 is 4-14 % behind there).
-    cosine_fine = loss == MAFED_LOSS_COSINE && pass != kPassFwd && (row_bytes >= 4096 || pass == kPassFused);
+    // Measured on B200 (profiles/r02l_geometry_sweep.txt: one-pass step, 13 shapes x 13 rings; r02q_geometry_sweep_
+    // {fwd,bwd}.txt: the two passes; all after the producer stopped paying 64-bit divisions and the mask round trip
+    // per tile).  What the memory system is sensitive to is the number of bytes in flight per SM:
+    //  * forward pass (reads only): 2 stages x 96 KB -- best or within 2 % for every shape; ragged long text +13 %
+    //    and cosine +5 % over 2 x 72 KB.
+    //  * passes that also write the gradient (backward, one-pass step): 3 stages x 32 KB (96 KB in flight) is the best
+    //    or within 2.5 % of it for every shape of 256 visual + ~32 text rows (base / 410M / 1B, bf16 and fp32, 16..256
+    //    samples), 5-12 % ahead of 2 x 64 KB; 64 KB in flight is latency-bound (+20 %), 128 KB and more queue up in
+    //    the memory system (+5-13 %).
+    //  * the cosine gradient needs two sweeps over a row with a warp reduction in between, so a stage drains more
+    //    slowly: 4 stages x 32 KB keep more rows in different phases at once.
+    //  * text-heavy batches (more than a quarter of the rows behind the attention mask, where ragged masks make
+    //    whole tiles zero-fill only) keep the coarse ring, 2 x 64-72 KB: fewer, larger tiles amortise the per-tile
+    //    cost of the padded ones (3 x 32 KB is 4-16 % behind there).
     const bool text_heavy = (long long)(sh.T - sh.n_vis) * 4 > (long long)sh.T;
-    fused_fine = !cosine_fine && pass == kPassFused && !text_heavy;
-    const long long stage_target = (cosine_fine || fused_fine) ? 32 * 1024 : 72 * 1024;
+    wide = pass == kPassFwd;
+    cosine_fine = !wide && loss == MAFED_LOSS_COSINE;
+    fused_fine = !wide && !cosine_fine && !text_heavy;
+    const long long stage_target = wide ? 96 * 1024 : ((cosine_fine || fused_fine) ? 32 * 1024 : 72 * 1024);
     rows = (int)(stage_target / (2 * row_bytes));
-    if (rows >= 8 && !fused_fine && !(cosine_fine && pass == kPassFused)) rows &= ~7;
+    if (rows >= 8 && !wide && !cosine_fine && !fused_fine) rows &= ~7;
   }
   if (rows > kTmaMaxRows) rows = kTmaMaxRows;
   if (rows < 1) rows = 1;
@@ -290,7 +294,7 @@ inline bool tma_geometry(const mafed_shape_t& sh, const PathParams& p, int pass,
   geo.rows = rows;
   geo.stage_bytes = (int)(2 * rows * row_bytes);
   int stages = tune(sh, kTuneTmaStages + pass);
-  if (stages <= 0) stages = cosine_fine ? 4 : (fused_fine ? 3 : ((2 * geo.stage_bytes >= 96 * 1024) ? 2 : 3));
+  if (stages <= 0) stages = cosine_fine ? 4 : (fused_fine ? 3 : ((wide || 2 * geo.stage_bytes >= 96 * 1024) ? 2 : 3));
   if (stages > kTmaMaxStages) stages = kTmaMaxStages;
   while (stages > 1 && (long long)stages * geo.stage_bytes > budget) --stages;
   geo.stages = stages;
@@ -301,7 +305,7 @@ inline bool tma_geometry(const mafed_shape_t& sh, const PathParams& p, int pass,
   const int pace = tune(sh, kTunePaceNs);
   geo.pace_ns = pace > 0 ? pace : 0;
   geo.pace_dense = 0;
-  if (pace == 0 && pass == kPassFused && !fused_fine && !cosine_fine && rows_default && stages_default) {
+  if (pace == 0 && pass != kPassFwd && !fused_fine && !cosine_fine && rows_default && stages_default) {
     geo.pace_ns = 500;
     geo.pace_dense = 1;
   }

@@ -2,7 +2,7 @@
 """Ring geometry of the fused TMA kernel (stage size x stages) against the kernel-level step time (fused kernel +
 gate, back to back), on the library MAFED_B200_LIB selects (default: the in-tree build).
 
-    python tools/geometry_sweep.py [rounds] [points] [geometries]
+    python tools/geometry_sweep.py [rounds] [points] [geometries] [fused|fwd|bwd]
 
 points: ';'-separated n_layers:B:txt:D:dtype:mask:loss; geometries: ','-separated KBxSTAGES[@PACE_NS] (stage size in KB
 of student + teacher rows; 0x0 = the library's default; PACE_NS = the producer's sleep before a refill).
@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from mafed_b200 import cabi  # noqa: E402
-from mafed_b200.distill_op import distill_backward, distill_fused  # noqa: E402
+from mafed_b200.distill_op import distill_backward, distill_forward, distill_fused  # noqa: E402
 
 POINTS = ("15:64:32:2048:bf16:ones:mse;15:64:32:2048:bf16:ragged:mse;15:64:256:2048:bf16:ones:mse;"
           "15:64:256:2048:bf16:ragged:mse;15:16:32:2048:bf16:ones:mse;15:128:128:2048:bf16:ragged:mse;"
@@ -51,6 +51,8 @@ def main():
         g, _, pace = g.partition("@")                   # KBxSTAGES[@pace_ns]
         kb, stages = (int(v) for v in g.split("x"))
         geos.append((kb, stages, int(pace or 0)))
+    which = sys.argv[4] if len(sys.argv) > 4 else "fused"
+    pass_index = {"fwd": 0, "bwd": 1, "fused": 2}[which]
     ctx = bench.Ctx(types.SimpleNamespace())
     dev = ctx.device
     for pt in points.split(";"):
@@ -67,21 +69,32 @@ def main():
         grads = [torch.empty_like(s) for s in st]
         gout = torch.ones((), dtype=torch.float32, device=dev)
 
+        held = []
+
         def step(i):
-            out, scale, ln = distill_fused(st, te, grads, masks[i % 2], plan, group=False)
-            distill_backward(ln, grads, scale, gout, skip_if_equals=plan.assumed_grad_out * plan.grad_multiplier,
-                             grad_out_scale=plan.grad_multiplier)
+            if which == "fused":
+                out, scale, ln = distill_fused(st, te, grads, masks[i % 2], plan, group=False)
+                distill_backward(ln, grads, scale, gout, skip_if_equals=plan.assumed_grad_out * plan.grad_multiplier,
+                                 grad_out_scale=plan.grad_multiplier)
+            elif which == "fwd":
+                distill_forward(st, te, masks[i % 2], plan, group=False)
+            else:
+                if not held:
+                    held.append(distill_forward(st, te, masks[0], plan, group=False))
+                out, scale, ln = held[0]
+                distill_backward(ln, grads, scale, gout, grad_out_scale=plan.grad_multiplier)
         est_ms = 3.0 * n * B * (bench.N_VIS + txt) * row_bytes / 6.5e9
         iters = max(20, min(100, int(40.0 / est_ms)))
         res = {}
         for _ in range(rounds):
             for kb, stages, pace in geos:
                 rows = max(1, kb * 1024 // (2 * row_bytes)) if kb else 0
-                with cabi.tuning(raw={cabi.TUNE_TMA_ROWS + FUSED: rows, cabi.TUNE_TMA_STAGES + FUSED: stages,
+                with cabi.tuning(raw={cabi.TUNE_TMA_ROWS + pass_index: rows, cabi.TUNE_TMA_STAGES + pass_index: stages,
                                       cabi.TUNE_PACE_NS: pace}):
+                    held.clear()        # (the launch record carries the tuning it was made under)
                     res.setdefault((kb, stages, rows, pace), []).append(time_ms(step, iters, 8))
         best = min(statistics.median(v) for v in res.values())
-        row = {"point": pt, "best_ms": round(best, 4)}
+        row = {"point": pt, "pass": which, "best_ms": round(best, 4)}
         for (kb, stages, rows, pace), v in res.items():
             row[f"{kb}x{stages}(r{rows})" + (f"@{pace}" if pace else "")] = round(statistics.median(v) / best, 3)
         print(json.dumps(row), flush=True)
