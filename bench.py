@@ -77,13 +77,22 @@ class ClockSampler:
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._stop = threading.Event()
+        self._go = threading.Event()
         self._thread = None
+        self._nv = self._handle = None
+        try:                                    # set up before the timed region: a 10 ms region must still be sampled
+            import pynvml as nv
+            nv.nvmlInit()
+            self._handle = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM)
+            self._nv = nv
+        except Exception:
+            self._nv = None
 
     def _loop_nvml(self):
-        import pynvml as nv
-        nv.nvmlInit()
-        h = nv.nvmlDeviceGetHandleByIndex(self.index)
-        self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        nv, h = self._nv, self._handle
+        if nv is None:
+            raise RuntimeError("no nvml")
         names = {
             getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
             getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
@@ -91,6 +100,8 @@ class ClockSampler:
             getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
             getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
         }
+        self._go.wait()                         # the thread exists before the barrier; it samples from `go()` on
+        time.sleep(0.001)                       # let the first launches reach the GPU
         while not self._stop.is_set():
             self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
             try:
@@ -100,13 +111,15 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            if self._stop.wait(0.003):
+                break
 
     def _loop_smi(self):
         import subprocess
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self._go.wait()
         while not self._stop.is_set():
             out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                  capture_output=True, text=True).stdout.strip().split(",")
@@ -130,8 +143,13 @@ class ClockSampler:
         self._thread.start()
         return self
 
+    def go(self):
+        """Start sampling: called right after the timed region's first event is recorded."""
+        self._go.set()
+
     def __exit__(self, *exc):
         self._stop.set()
+        self._go.set()
         self._thread.join(timeout=5)
 
     def summary(self):
@@ -341,11 +359,22 @@ class Ctx:
             dist.init_process_group("nccl", device_id=self.device)
         self.peak, self.peak_src = peaks()
 
-    def sync_all(self):
+    def sync_all(self, align=False):
+        """Barrier + device synchronize.  ``align``: the ranks additionally leave together -- NCCL's barrier lets them go
+        ~160 us apart (measured: `start_skew.barrier_exit_spread_us` before this was added), which a K-step timed
+        region of a coupled step pays once, i.e. 8 us per step at K = 20; so they agree on a moment of the system-wide
+        monotonic clock 300 us after the last one arrived and spin until then."""
         torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier()
             torch.cuda.synchronize()
+            if align:
+                t = torch.tensor([time.perf_counter()], dtype=torch.float64, device=self.device)
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+                go_at = float(t) + 300e-6
+                torch.cuda.synchronize()
+                while time.perf_counter() < go_at:
+                    pass
 
     def max_over_ranks(self, values):
         t = torch.tensor(list(values), dtype=torch.float64, device=self.device)
@@ -356,29 +385,38 @@ class Ctx:
 
 class ApiLoop:
     """The user's call, step after step: ``fd.distill(output, batch)`` then ``loss.backward()``.  Across batch shards
-    the token counts of the NEXT batch leave for the peers while the current step runs (``fd.prefetch_counts``, what
-    ``replay`` does as soon as it has drawn a memory batch): two mask tensors alternate so that a prefetched batch
-    is a different object from the one being consumed."""
+    the token counts of a batch leave for the peers when the batch is "drawn" (``fd.prefetch_counts``, what ``replay``
+    does as soon as it has a memory batch, a whole student forward ahead of ``distill``).  There is no forward here,
+    so the loop draws two batches ahead: once step i is launched it sends the counts of batch i+2; the 1-CTA prefetch
+    (ordered behind the work already on the stream, because it reads the mask) then runs beside step i+1 and never
+    sits between two steps.  Three mask tensors rotate so that a prefetched batch is a different object from the ones
+    in use."""
 
     def __init__(self, ctx, fd, leaves, masks):
-        self.ctx, self.fd, self.leaves, self.masks = ctx, fd, leaves, masks
+        self.ctx, self.fd, self.leaves = ctx, fd, leaves
+        self.prefetch = ctx.world > 1
+        self.masks = list(masks) + ([masks[0].clone()] if self.prefetch else [])
         self.out = Out(tuple(leaves))
         self.i = 0
-        self.prefetch = ctx.world > 1
 
     def prime(self):
         if self.prefetch and self.fd.process_group is not False:
-            self.fd.prefetch_counts({"attention_mask": self.masks[self.i % 2]})
+            n = len(self.masks)
+            for m in (self.masks[self.i % n], self.masks[(self.i + 1) % n]):
+                tk = self.fd._tickets.get(id(m))
+                if tk is None or tk[0] is not m or tk[1] != m._version:      # (still in flight from the last loop)
+                    self.fd.prefetch_counts({"attention_mask": m})
 
     def step(self):
         fd, i = self.fd, self.i
         self.i += 1
         for s in self.leaves:
             s.grad = None
-        if self.prefetch and fd.process_group is not False:
-            fd.prefetch_counts({"attention_mask": self.masks[(i + 1) % 2]})
-        loss = fd.distill(self.out, {"attention_mask": self.masks[i % 2]})
+        n = len(self.masks)
+        loss = fd.distill(self.out, {"attention_mask": self.masks[i % n]})
         loss.backward()
+        if self.prefetch and fd.process_group is not False:
+            fd.prefetch_counts({"attention_mask": self.masks[(i + 2) % n]})
         return loss
 
     def timed(self, steps, warmup, sampler=None):
@@ -387,14 +425,18 @@ class ApiLoop:
         for _ in range(warmup):
             self.step()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        self.ctx.sync_all()
         cm = sampler if sampler is not None else _Null()
-        with cm:
+        with cm:        # (the sampler's thread is created before the barrier, so that the ranks leave it together)
+            self.ctx.sync_all(align=True)
             t0 = time.perf_counter()
             e0.record()
-            for _ in range(steps):
+            cm.go()
+            for k in range(steps):
                 loss = self.step()
+                if k == 0:
+                    self.first_step_enqueued_us = (time.perf_counter() - t0) * 1e6
             e1.record()
+            self.t0_monotonic = t0
             host_us = (time.perf_counter() - t0) / steps * 1e6   # CPU time to enqueue one step (no sync inside)
             self.ctx.sync_all()
         return e0.elapsed_time(e1), host_us, loss
@@ -403,6 +445,9 @@ class ApiLoop:
 class _Null:
     def __enter__(self):
         return self
+
+    def go(self):
+        pass
 
     def __exit__(self, *exc):
         return False
@@ -899,6 +944,16 @@ def run_main(ctx):
     trace0 = peer.trace() if peer is not None else None
     sampler = ClockSampler(ctx.local_rank)
     api_ms, host_us, loss = loop.timed(args.steps, args.warmup, sampler)
+    start_skew = None
+    if world > 1:
+        # how far apart the ranks left the barrier (CLOCK_MONOTONIC is system-wide) and how long each took to enqueue
+        # its first step: with K timed steps this one-time skew is charged to the coupled step as skew / K
+        mine = torch.tensor([loop.t0_monotonic, loop.first_step_enqueued_us], dtype=torch.float64, device=device)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        t0s = [float(x[0]) for x in every]
+        start_skew = {"barrier_exit_spread_us": (max(t0s) - min(t0s)) * 1e6,
+                      "first_step_enqueued_us_per_rank": [float(x[1]) for x in every]}
     trace1 = peer.trace() if peer is not None else None
     uncoupled = None
     if world > 1:
@@ -1012,6 +1067,8 @@ def run_main(ctx):
                                   "the slowest GPU every step: ms_per_step vs max(uncoupled) is the cost of the exchange "
                                   "itself, max(uncoupled) vs the 1-GPU run is GPU-to-GPU variation")
     line["clocks"] = sampler.summary()
+    if start_skew is not None:
+        line["start_skew"] = start_skew
     # the API loop against the kernel-level loop (fused + gate), same interleaved rounds
     line["api_minus_kernel_loop_us"] = api_minus_kernel_us if world == 1 else None
 
