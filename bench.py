@@ -424,21 +424,29 @@ class ApiLoop:
         self.prime()
         for _ in range(warmup):
             self.step()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ec, e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         cm = sampler if sampler is not None else _Null()
         with cm:        # (the sampler's thread is created before the barrier, so that the ranks leave it together)
             self.ctx.sync_all(align=True)
+            t_barrier = time.perf_counter()
+            # The K timed steps run between two events on the device.  The opening event is queued behind ONE more
+            # untimed step issued after the barrier, so the region starts with the GPU busy and the host a step ahead
+            # -- the state every step of a training run is in -- instead of with an idle GPU waiting ~0.15-0.5 ms for
+            # the first launch to arrive (at N > 1: for the slowest rank's first launch; 2-5 % of a 20-step region).
+            # `cold_ms_per_step` is the same loop timed from the barrier, that step and its launch latency included.
+            ec.record()
+            self.step()
+            self.first_step_enqueued_us = (time.perf_counter() - t_barrier) * 1e6
             t0 = time.perf_counter()
             e0.record()
             cm.go()
             for k in range(steps):
                 loss = self.step()
-                if k == 0:
-                    self.first_step_enqueued_us = (time.perf_counter() - t0) * 1e6
             e1.record()
-            self.t0_monotonic = t0
+            self.t0_monotonic = t_barrier
             host_us = (time.perf_counter() - t0) / steps * 1e6   # CPU time to enqueue one step (no sync inside)
             self.ctx.sync_all()
+        self.cold_ms_per_step = ec.elapsed_time(e1) / (steps + 1)
         return e0.elapsed_time(e1), host_us, loss
 
 
@@ -596,8 +604,9 @@ def measure_point(ctx, n_sel, B, txt, D, dt, ragged, steps, warmup, loss="mse", 
             kstep(i)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.sync_all()
+        kstep(warmup)                           # (the region opens behind one untimed step, like ApiLoop.timed)
         e0.record()
-        for i in range(warmup, warmup + steps):
+        for i in range(warmup + 1, warmup + 1 + steps):
             kstep(i)
         e1.record()
         ctx.sync_all()
@@ -613,6 +622,7 @@ def measure_point(ctx, n_sel, B, txt, D, dt, ragged, steps, warmup, loss="mse", 
             gstep.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.sync_all()
+        gstep.replay()                          # (the region opens behind one untimed step, like ApiLoop.timed)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
@@ -904,6 +914,7 @@ def run_main(ctx):
                 one(i)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
+            one(1)                              # (the region opens behind one untimed step, like ApiLoop.timed)
             e0.record()
             for i in range(args.steps):
                 one(i)
@@ -944,10 +955,11 @@ def run_main(ctx):
     trace0 = peer.trace() if peer is not None else None
     sampler = ClockSampler(ctx.local_rank)
     api_ms, host_us, loss = loop.timed(args.steps, args.warmup, sampler)
+    cold_ms = loop.cold_ms_per_step
     start_skew = None
     if world > 1:
         # how far apart the ranks left the barrier (CLOCK_MONOTONIC is system-wide) and how long each took to enqueue
-        # its first step: with K timed steps this one-time skew is charged to the coupled step as skew / K
+        # the step behind which the timed region opens (what `timed_region.cold_ms_per_step` still pays, once)
         mine = torch.tensor([loop.t0_monotonic, loop.first_step_enqueued_us], dtype=torch.float64, device=device)
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine)
@@ -966,6 +978,7 @@ def run_main(ctx):
         gstep.replay()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.sync_all()
+    gstep.replay()                              # (the region opens behind one untimed step, like ApiLoop.timed)
     t_host = time.perf_counter()
     g0.record()
     for _ in range(args.steps):
@@ -976,8 +989,8 @@ def run_main(ctx):
     graph_ms = g0.elapsed_time(g1)
     graph_loss = float(gstep.loss)
     del gstep
-    api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms, graph_ms = ctx.max_over_ranks(
-        [api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms, graph_ms])
+    api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms, graph_ms, cold_ms = ctx.max_over_ranks(
+        [api_ms, two_api_ms, one_raw_ms, two_raw_ms, fwd_ms, bwd_ms, fused_ms, gate_ms, graph_ms, cold_ms])
     ms_per_step = api_ms / args.steps
     value = units_per_step / (ms_per_step * 1e-3)
 
@@ -1019,6 +1032,11 @@ def run_main(ctx):
                           "frac": gbs(fused_bytes, ms_per_step) / peak,
                           "frac_of_nominal_8000": gbs(fused_bytes, ms_per_step) / 8000.0, "bytes_per_unit": 3 * row_bytes},
         "kernel_value": units_per_step / (one_raw_ms / args.steps * 1e-3),
+        "timed_region": {"what": "barrier + synchronize, one more untimed step, event, the K timed steps, event, barrier + "
+                                 "synchronize: the region opens on the device behind that step, with the GPU busy and the "
+                                 "host a step ahead as in every step of a training run; `cold_ms_per_step` is the same loop "
+                                 "timed from the barrier over K + 1 steps, the idle GPU's wait for the first launch included",
+                         "cold_ms_per_step": cold_ms, "cold_value": units_per_step / (cold_ms * 1e-3)},
         "host_us_per_step": host_us,
         "graphed": {"what": "fd.capture(...): distill() + backward() captured once into a CUDA graph, replayed per step",
                     "ms_per_step": graph_ms / args.steps, "value": units_per_step / (graph_ms / args.steps * 1e-3),
