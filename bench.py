@@ -419,8 +419,9 @@ class ApiLoop:
             fd.prefetch_counts({"attention_mask": self.masks[(i + 2) % n]})
         return loss
 
-    def timed(self, steps, warmup, sampler=None):
-        """(GPU ms for `steps` steps, host us per step to enqueue one, last loss)."""
+    def timed(self, steps, warmup, sampler=None, snapshot=None):
+        """(GPU ms for `steps` steps, host us per step to enqueue one, last loss).  ``snapshot(k)``: called with 0
+        where the timed region opens and 1 where it closes (stream-ordered diagnostics; must not synchronise)."""
         self.prime()
         for _ in range(warmup):
             self.step()
@@ -439,10 +440,14 @@ class ApiLoop:
             self.first_step_enqueued_us = (time.perf_counter() - t_barrier) * 1e6
             t0 = time.perf_counter()
             e0.record()
+            if snapshot is not None:
+                snapshot(0)
             cm.go()
             for k in range(steps):
                 loss = self.step()
             e1.record()
+            if snapshot is not None:
+                snapshot(1)
             self.t0_monotonic = t_barrier
             host_us = (time.perf_counter() - t0) / steps * 1e6   # CPU time to enqueue one step (no sync inside)
             self.ctx.sync_all()
@@ -952,9 +957,13 @@ def run_main(ctx):
 
     # (the uncoupled loop runs before AND after the coupled one: step times drift by ~1 % as the GPUs warm up)
     uncoupled_before = uncoupled_loop() if world > 1 else None
-    trace0 = peer.trace() if peer is not None else None
+    # SM cycles the in-kernel exchanges take on rank 0: two stream-ordered snapshots of the communicator's counters
+    # (mafed_comm_trace_async), taken where the timed region opens and closes -- exactly the K timed steps
+    trace_buf = torch.zeros((2, 4), dtype=torch.int64).pin_memory() if peer is not None else None
+    snapshot = (lambda k: peer.trace_into(trace_buf[k])) if peer is not None else None
     sampler = ClockSampler(ctx.local_rank)
-    api_ms, host_us, loss = loop.timed(args.steps, args.warmup, sampler)
+    api_ms, host_us, loss = loop.timed(args.steps, args.warmup, sampler, snapshot)
+    trace0, trace1 = (trace_buf[0].tolist(), trace_buf[1].tolist()) if peer is not None else (None, None)
     cold_ms = loop.cold_ms_per_step
     start_skew = None
     if world > 1:
@@ -966,7 +975,6 @@ def run_main(ctx):
         t0s = [float(x[0]) for x in every]
         start_skew = {"barrier_exit_spread_us": (max(t0s) - min(t0s)) * 1e6,
                       "first_step_enqueued_us_per_rank": [float(x[1]) for x in every]}
-    trace1 = peer.trace() if peer is not None else None
     uncoupled = None
     if world > 1:
         uncoupled_after = uncoupled_loop()
@@ -1076,7 +1084,7 @@ def run_main(ctx):
             "counts_exchange_in_fused_kernel": (trace1[0] - trace0[0]) / calls / mhz,
             "sums_publish_in_tail": (trace1[1] - trace0[1]) / calls / mhz,
             "sums_wait_for_peers_in_tail": (trace1[2] - trace0[2]) / calls / mhz,
-            "steps_traced": calls, "includes_warmup": True}
+            "steps_traced": calls, "includes_warmup": False}
     if uncoupled is not None:
         line["uncoupled_ms_per_rank"] = uncoupled
         line["uncoupled_ms_per_rank_before_after"] = [uncoupled_before, uncoupled_after]

@@ -126,6 +126,9 @@ int mafed_comm_status(mafed_comm_t* comm, int* status_out /* 0 ok, 1 a peer time
 /* SM-cycle totals since creation (synchronises the device): [0] in-kernel counts exchange as seen by CTA 0,
  * [1] own peer stores of a sums exchange, [2] waiting for the peers' vectors, [3] sums exchanges. */
 int mafed_comm_trace(mafed_comm_t* comm, unsigned long long* out4);
+/* The same four totals as a stream-ordered snapshot: an asynchronous copy into `out4` (pinned host or device memory)
+ * behind the work already queued on `stream`; no synchronisation.  Two snapshots bracket the steps between them. */
+int mafed_comm_trace_async(mafed_comm_t* comm, unsigned long long* out4, void* stream);
 int mafed_comm_destroy(mafed_comm_t* comm);
 
 /* Token counts ahead of the step.  The counts depend only on the attention mask, which is known when the memory

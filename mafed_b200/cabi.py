@@ -40,6 +40,7 @@ EXPORTS = (
     "mafed_distill_fwd", "mafed_distill_fused", "mafed_distill_scalar_stage",
     "mafed_distill_modality_masks", "mafed_distill_token_norm_sums",
     "mafed_comm_handle_bytes", "mafed_comm_create", "mafed_comm_connect", "mafed_comm_status", "mafed_comm_trace",
+    "mafed_comm_trace_async",
     "mafed_comm_set_timeout", "mafed_comm_destroy",
     "mafed_host_step_device_bytes", "mafed_host_step_create", "mafed_host_step_run", "mafed_host_step_destroy",
     "mafed_host_register", "mafed_host_unregister",
@@ -156,6 +157,8 @@ def load():
         lib.mafed_comm_status.argtypes = [vp, ctypes.POINTER(i32)]
         lib.mafed_comm_trace.restype = i32
         lib.mafed_comm_trace.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong)]
+        lib.mafed_comm_trace_async.restype = i32
+        lib.mafed_comm_trace_async.argtypes = [vp, vp, vp]
         lib.mafed_comm_set_timeout.restype = i32
         lib.mafed_comm_set_timeout.argtypes = [vp, ctypes.c_double]
         lib.mafed_comm_destroy.restype = i32

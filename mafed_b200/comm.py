@@ -50,6 +50,13 @@ class PeerComm:
         cabi.check(cabi.load().mafed_comm_trace(self.handle, out), "mafed_comm_trace")
         return list(out)
 
+    def trace_into(self, out4: torch.Tensor):
+        """The same four totals as a stream-ordered snapshot: an asynchronous copy into ``out4`` (a pinned or device
+        uint64/int64 tensor of 4 elements) behind the work queued on the current stream; no synchronisation."""
+        assert out4.numel() >= 4 and out4.element_size() == 8 and out4.is_contiguous()
+        cabi.check(cabi.load().mafed_comm_trace_async(self.handle, out4.data_ptr(),
+                                                      torch.cuda.current_stream().cuda_stream), "mafed_comm_trace_async")
+
     def close(self):
         if self.handle:
             cabi.load().mafed_comm_destroy(self.handle)

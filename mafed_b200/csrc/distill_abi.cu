@@ -337,6 +337,13 @@ int mafed_comm_trace(mafed_comm_t* c, unsigned long long* out4) {
   return (int)cudaMemcpy(out4, tail + 32, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
 }
 
+int mafed_comm_trace_async(mafed_comm_t* c, unsigned long long* out4, void* stream) {
+  if (!c || !out4) return MAFED_E_ARG;
+  const char* tail = reinterpret_cast<const char*>(c->local) + kCommTailAt;
+  return (int)cudaMemcpyAsync(out4, tail + 32, 4 * sizeof(unsigned long long), cudaMemcpyDefault,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int mafed_comm_destroy(mafed_comm_t* c) {
   if (!c) return 0;
   for (int r = 0; r < c->world; ++r)

@@ -22,7 +22,7 @@ EXPECTED_EXPORTS = sorted([
     "mafed_distill_out_len", "mafed_distill_step", "mafed_distill_fwd_step", "mafed_distill_bwd",
     "mafed_distill_prefetch_counts", "mafed_distill_fwd", "mafed_distill_fused", "mafed_distill_scalar_stage",
     "mafed_distill_modality_masks", "mafed_distill_token_norm_sums", "mafed_comm_handle_bytes", "mafed_comm_create",
-    "mafed_comm_connect", "mafed_comm_status", "mafed_comm_trace", "mafed_comm_set_timeout", "mafed_comm_destroy",
+    "mafed_comm_connect", "mafed_comm_status", "mafed_comm_trace", "mafed_comm_trace_async", "mafed_comm_set_timeout", "mafed_comm_destroy",
     "mafed_host_step_device_bytes", "mafed_host_step_create", "mafed_host_step_run", "mafed_host_step_destroy",
     "mafed_host_register", "mafed_host_unregister"])
 
@@ -103,6 +103,7 @@ def test_argument_errors_without_a_gpu():
                                           None) == -1
     assert lib.mafed_distill_fwd_step(ctypes.byref(ok), None, None, None, None, None, None, None, None, None, None) == -1
     assert lib.mafed_comm_trace(None, None) == -1
+    assert lib.mafed_comm_trace_async(None, None, None) == -1
 
 
 def test_sass_is_sm100_and_uses_bulk_copies():
