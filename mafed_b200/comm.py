@@ -27,7 +27,8 @@ class PeerComm:
         self.handle, self.world, self.rank = handle, world, rank
 
     def status(self) -> int:
-        """0 = ok, 1 = a peer did not arrive within the spin bound (synchronises the device)."""
+        """0 = ok, 1 = a peer did not arrive within the spin bound.  A plain read of a word in mapped pinned host
+        memory (no synchronisation): it reflects every exchange of the kernels that have finished."""
         out = ctypes.c_int(0)
         cabi.check(cabi.load().mafed_comm_status(self.handle, ctypes.byref(out)), "mafed_comm_status")
         return out.value
@@ -38,7 +39,8 @@ class PeerComm:
 
     def check(self):
         """Raise if a peer did not arrive within the spin bound in any exchange so far (the losses and gradients
-        of that step are NaN).  Synchronises the device: call it where the host reads results anyway."""
+        of that step are NaN).  Does not synchronise: it sees the kernels that have finished; synchronise the stream
+        first for a verdict on the steps still queued."""
         if self.status() != 0:
             raise cabi.MafedDistillError(
                 f"rank {self.rank}: a peer did not reach a distillation exchange within the spin bound "
