@@ -71,3 +71,51 @@ def test_random_configuration(seed):
             assert rel_err(gpu.float(), r.float()) <= gtol, (c, i)
         zero_rows = r.float().abs().amax(-1) == 0
         assert bool((gpu.float().abs().amax(-1)[zero_rows] == 0).all()), c
+
+
+@pytest.mark.parametrize("seed", range(100, 132))
+def test_random_configuration_against_the_reference_on_this_gpu(seed):
+    """The same sweep against the UNMODIFIED reference (``oracle/_ref``, shipped with the snapshot) run on this GPU
+    on the same tensors -- under ``torch.autocast("cuda", bfloat16)`` for bf16 inputs, as ``replay()`` runs it
+    (``distillation.py:90``): the like-for-like check of SURVEY 8(c), no oracle in between."""
+    from oracle import ref_harness as R
+    if not R.available():
+        pytest.skip("oracle/_ref is absent: run `python oracle/make_ref.py` in the build container")
+    c = _case(seed)
+    if c["dtype"] == torch.float16:
+        c["dtype"] = torch.bfloat16                                 # (the reference never feeds fp16)
+    st, te, am = O.make_inputs(c["nh"] + 1, c["bsz"], c["txt"], c["dim"], n_vis=c["n_vis"], dtype=c["dtype"],
+                               seed=c["seed"], teacher=c["teacher"], mask="ragged" if c["mask"] == "ragged" else "full")
+    if c["mask"] in ("random", "sparse"):
+        am = (torch.rand(am.shape, generator=torch.Generator().manual_seed(seed)) > 0.4).long()
+    if int(am.sum()) == 0:
+        am[0, -1] = 1
+    meta = dict(modality=c["modality"], layer_strategy=c["layer_strategy"], loss=c["loss"], gamma=c["gamma"],
+                num_hidden_layers=c["nh"], layer=c["layer"], n_vis=c["n_vis"], coeff=c["coeff"], cls=False,
+                lang_coeff=c["lang_coeff"])
+    fd = R.make_reference_method(modality=c["modality"], layer_strategy=c["layer_strategy"], loss=c["loss"],
+                                 gamma=c["gamma"], num_hidden_layers=c["nh"], layer=c["layer"], coeff=c["coeff"],
+                                 n_vis=c["n_vis"], lang_coeff=c["lang_coeff"])
+    if c["lang_coeff"] is not None:
+        fd.loss_weights.lang_coeff = fd.loss_weights.lang_coeff.cuda()
+    ref = R.reference_forward_backward(fd, [s.cuda() for s in st], [t.cuda() for t in te], am.cuda(),
+                                       grad_out=c["grad_out"], autocast_bf16=c["dtype"] != torch.float32)
+    out = run_product(meta, st, te, am, grad_out=c["grad_out"], variant=c["variant"], single_pass=c["single_pass"],
+                      accumulate=c["accumulate"])
+    ltol, gtol = tolerances(c["dtype"])
+    assert float(out["loss"]) == pytest.approx(float(ref["loss"]), rel=ltol, abs=1e-12), c
+    # the masks the reference leaves in `batch` (distillation.py:139,144) and the values it sends to W&B (:165)
+    assert torch.equal(out["batch"]["lang_masks"].cpu(), ref["batch"]["lang_masks"].cpu().long())
+    assert torch.equal(out["batch"]["image_masks"].cpu(), ref["batch"]["image_masks"].cpu().long())
+    assert "labels" not in out["batch"] and "labels" not in ref["batch"]
+    mine = out["layer_dict"]
+    assert sorted(mine) == sorted(ref["logged"]), c
+    for k, v in ref["logged"].items():
+        assert mine[k] == pytest.approx(v, rel=ltol, abs=1e-12), (c, k)
+    for i, r in enumerate(ref["grads"]):
+        if r is None:
+            assert out["grads"][i] is None, c
+            continue
+        gpu = out["grads"][i]
+        assert gpu.dtype == c["dtype"]
+        assert rel_err(gpu.float(), r.float().cpu()) <= gtol, (c, i)
